@@ -1,0 +1,197 @@
+/*
+ * v3d_b200.h -- C-ABI of the B200-native (sm_100a) vision3d per-frame LiDAR hot path.
+ *
+ * This is the drop-in boundary. The reference (jhultman/vision3d @ b9a50ee) has no C plugin
+ * registry; its boundary is four Python import names. Each entry point
+ * below is what a binding for one of those names calls; the reference interface it replaces
+ * is cited as file:line relative to the reference tree. INTEGRATION.md shows the ctypes stubs.
+ *
+ * Conventions (mirroring the in-tree reference ops, SURVEY.md 8b "Conventions"):
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; inputs are never
+ *     mutated; outputs and workspaces are caller-allocated (no allocation inside the library);
+ *   - `stream` is a cudaStream_t passed as void* (the reference launches on the current
+ *     torch stream: box_iou_rotated_cuda.cu:71,102); calls are asynchronous and never
+ *     synchronise the stream or the device, so the whole path can be CUDA-graph captured;
+ *   - data-dependent sizes (kept boxes, voxels, active sites) are written to DEVICE counters
+ *     and the outputs are sized by a static capacity, instead of the reference's blocking
+ *     D2H copy (nms_rotated_cuda.cu:106);
+ *   - return value: V3D_OK (0) or a negative v3d error; on error nothing is launched.
+ *     The reference raises RuntimeError through AT_ASSERTM/AT_ERROR
+ *     (box_iou_rotated_cuda.cu:69-70,85-87); the Python bindings do the same from the code.
+ *   - fp32 data, int32 indices, row-major contiguous, exactly as the reference ops read them
+ *     through raw data_ptr (box_iou_rotated_cuda.cu:81-82).
+ *   - there is NO CPU path: every function needs a CUDA device of compute capability 10.x.
+ */
+#ifndef V3D_B200_H_
+#define V3D_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define V3D_API
+#else
+#define V3D_API __attribute__((visibility("default")))
+#endif
+
+typedef void* v3d_stream_t; /* cudaStream_t */
+
+enum {
+  V3D_OK = 0,
+  V3D_ERR_INVALID_ARGUMENT = -1,  /* bad size / null pointer / unsupported channel count */
+  V3D_ERR_WORKSPACE_TOO_SMALL = -2,
+  V3D_ERR_CUDA = -3,              /* a CUDA runtime call or launch failed (see v3d_last_cuda_error) */
+  V3D_ERR_UNSUPPORTED_DEVICE = -4 /* not an sm_100 class device */
+};
+
+V3D_API int v3d_abi_version(void);
+V3D_API const char* v3d_status_string(int status);
+V3D_API const char* v3d_last_cuda_error(void);
+/* cuda_version.cu / vision.cpp:21-32 get_cuda_version(): CUDART_VERSION the library was built with */
+V3D_API int v3d_cudart_version(void);
+/* 0 if the current device can run this library (compute capability 10.x), else an error */
+V3D_API int v3d_check_device(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * a13  box_iou_rotated(boxes1[M,5], boxes2[N,5]) -> ious[M,N]
+ * replaces vision3d._C.box_iou_rotated: csrc/vision.cpp:63, box_iou_rotated.h:20-32,
+ * box_iou_rotated_cuda.cu:65-121. Boxes are (x_ctr, y_ctr, w, h, angle_degrees).
+ * Arithmetic = single_box_iou_rotated as nvcc compiles it (box_iou_rotated_utils.h:313-340,
+ * exchange-sort hull :197-214) evaluated WITHOUT fused multiply-add, i.e. bit-identical to
+ * oracle variant 1 / the header compiled on the host.
+ * ------------------------------------------------------------------------------------------- */
+V3D_API int v3d_box_iou_rotated(const float* boxes1, int M, const float* boxes2, int N, float* ious,
+                                v3d_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a12  nms_rotated(dets[N,5], scores[N], thr) -> keep (indices into dets, descending score)
+ * replaces vision3d._C.nms_rotated: csrc/vision.cpp:64, nms_rotated.h:22-36,
+ * nms_rotated_cuda.cu:74-134 (bit set when IoU > thr, greedy scan over the sorted list).
+ * Everything stays on the device: score ranking (stable: ties -> lower index first), upper-
+ * triangular 64x64 mask tiles with an exact disjointness pre-test, and the greedy scan.
+ * keep[0..*num_keep) is valid, keep must hold N int64; num_keep is one device int32.
+ * ------------------------------------------------------------------------------------------- */
+V3D_API size_t v3d_nms_rotated_workspace_bytes(int N);
+V3D_API int v3d_nms_rotated(const float* dets, const float* scores, int N, float iou_threshold,
+                            int64_t* keep, int* num_keep, void* workspace, size_t workspace_bytes,
+                            v3d_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a1 (+a2)  point -> voxel for a whole batch in one call
+ * replaces spconv.utils.VoxelGenerator(...).generate(points) per frame and the batch-index
+ * prefix + concatenate of Preprocessor.generate_batch_voxels (core/preprocess.py:17-33), and
+ * optionally VoxelFeatureExtractor.forward (detector/layers.py:10-17) as an epilogue.
+ *   points        (total_points, C) f32, frames concatenated; first 3 columns are x,y,z
+ *   frame_offsets (B+1) int32 device: frame b owns rows [off[b], off[b+1])
+ *   max_frame_points  HOST upper bound on any frame's point count (<= total_points); sizes the grid
+ *   points_capacity   the capacity the workspace was sized/initialised with (>= total_points)
+ *   range_min[3], voxel_size[3] fp32 (xyz) and grid[3] cells per axis (xyz) are HOST values
+ *   cap_policy    0 = stop the frame at the first point that would open voxel #max_voxels
+ *                 (spconv v1.0/1.1), 1 = skip only such points (spconv >= 1.2)
+ * outputs (capacity B*max_voxels rows; frames packed back to back like np.concatenate):
+ *   voxels     (rows, max_pts, C) f32 zero padded, arrival order inside a voxel
+ *   coords     (rows, 4) int32 (b, z, y, x); voxel order = first appearance inside the frame
+ *   num_points (rows) int32
+ *   voxel_offsets (B+1) int32 device: frame b owns voxel rows [vo[b], vo[b+1])
+ *   mean       (rows, C) f32 = sum over slots / num_points, or NULL to skip (a2)
+ * The workspace is persistent: initialise once with v3d_voxelize_workspace_init and pass the
+ * same buffer to every call (it carries an epoch so no per-call clearing is needed); it must be
+ * re-initialised after 2^24-2 calls.
+ * ------------------------------------------------------------------------------------------- */
+V3D_API size_t v3d_voxelize_workspace_bytes(int total_points_capacity, int B);
+V3D_API int v3d_voxelize_workspace_init(void* workspace, size_t workspace_bytes,
+                                        int total_points_capacity, int B, v3d_stream_t stream);
+V3D_API int v3d_voxelize_batch(const float* points, int total_points, int max_frame_points, int C,
+                               const int* frame_offsets, int B, const float* range_min_host,
+                               const float* voxel_size_host,
+                               const int* grid_host, int max_pts, int max_voxels, int cap_policy,
+                               float* voxels, int* coords, int* num_points, int* voxel_offsets,
+                               float* mean, void* workspace, size_t workspace_bytes,
+                               int points_capacity, v3d_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a4  rule book (spconv get_indice_pairs inside SubMConv3d / SparseConv3d.forward; layers
+ * constructed at detector/sparse_cnn.py:15-30,151-175).
+ * The rule table is output-stationary: nbr[kk * nbr_stride + o] = input row feeding output row
+ * o through kernel offset kk = (kz*k1 + ky)*k2 + kx, or -1. Correlation convention of
+ * torch.nn.functional.conv3d: in_pos = out_pos*stride - pad + k*dilation.
+ * Active-site counts live on the device (n_in / n_out are device int32) so no host sync.
+ *
+ * A "site table" is a device hash of the active sites of one resolution level; it is built once
+ * per level and shared by every SubM layer with the same indice_key and by the strided conv
+ * that leaves the level.
+ * ------------------------------------------------------------------------------------------- */
+V3D_API size_t v3d_site_table_bytes(int capacity_rows);
+V3D_API int v3d_site_table_init(void* table, size_t table_bytes, int capacity_rows, v3d_stream_t stream);
+/* indices (cap,4) int32 b,z,y,x ; n_rows device int32 ; shape[3] (z,y,x) host */
+V3D_API int v3d_site_table_build(void* table, const int* indices, const int* n_rows, int capacity_rows,
+                                 const int* shape_host, v3d_stream_t stream);
+/* SubM: outputs = inputs. nbr (KV, nbr_stride). */
+V3D_API int v3d_rulebook_subm(const void* table, const int* indices, const int* n_rows,
+                              int capacity_rows, const int* shape_host, const int* ksize_host,
+                              const int* dilation_host, int* nbr, int nbr_stride, v3d_stream_t stream);
+/* Strided conv: discovers the output sites (ascending flat (b,z,y,x) order), writes
+ * out_indices (out_capacity,4), n_out (device) and nbr (KV, nbr_stride). in_table is the site
+ * table of the INPUT level. workspace from v3d_rulebook_conv_workspace_bytes. */
+V3D_API size_t v3d_rulebook_conv_workspace_bytes(int B, const int* out_shape_host, int capacity_rows,
+                                                 int kernel_volume);
+V3D_API void v3d_conv_out_shape(const int* shape, const int* ksize, const int* stride, const int* pad,
+                                const int* dilation, int* out_shape);
+V3D_API int v3d_rulebook_conv(const void* in_table, const int* indices, const int* n_rows,
+                              int capacity_rows, int B, const int* shape_host, const int* ksize_host,
+                              const int* stride_host, const int* pad_host, const int* dilation_host,
+                              int* out_indices, int* n_out, int out_capacity, int* nbr, int nbr_stride,
+                              void* workspace, size_t workspace_bytes, v3d_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a5 + a6  sparse convolution forward with the eval-mode BatchNorm1d + ReLU that
+ * spconv.SparseSequential applies next folded into the epilogue
+ * (SubMConvFunction / SparseConvFunction.forward; detector/sparse_cnn.py:15-30).
+ *   feat (n_in rows, Cin) f32, weight (KV, Cin, Cout) f32 [spconv layout (k0,k1,k2,Cin,Cout)],
+ *   out (out rows, Cout) f32 = relu?(scale * sum_kk feat[nbr[kk][o]] @ W[kk] + shift).
+ *   scale/shift may be NULL (identity); n_out is a device int32.
+ * ------------------------------------------------------------------------------------------- */
+V3D_API int v3d_sparse_conv_fwd(const float* feat, const float* weight, const int* nbr, int nbr_stride,
+                                const int* n_out, int out_capacity, int kernel_volume, int Cin,
+                                int Cout, const float* scale, const float* shift, int relu, float* out,
+                                v3d_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a3  SparseConvTensor.dense(): (N,C) rows -> (B,C,D,H,W), zero filled (sparse_cnn.py:128-133).
+ * workspace holds the (B,D,H,W) int32 cell->row map.
+ * ------------------------------------------------------------------------------------------- */
+V3D_API size_t v3d_sparse_to_dense_workspace_bytes(int B, const int* shape_host);
+V3D_API int v3d_sparse_to_dense(const float* feat, const int* indices, const int* n_rows,
+                                int capacity_rows, int C, int B, const int* shape_host, float* out,
+                                void* workspace, size_t workspace_bytes, v3d_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a7  furthest_point_sample(xyz[B,N,3], m) -> idx[B,m] int32   (detector/model.py:53)
+ * a8  gather_operation(feat[B,C,N], idx[B,m]) -> [B,C,m]          (detector/model.py:54)
+ * a9  ball_query(radius, nsample, xyz[B,N,3], new_xyz[B,M,3]) -> idx[B,M,nsample] int32
+ * a10 grouping_operation(feat[B,C,N], idx[B,M,ns]) -> [B,C,M,ns]
+ *     query_and_group: [xyz[idx]-new_xyz ; feat[idx]] -> [B,3+C,M,ns] (QueryAndGroup, use_xyz)
+ * (pointnet2 ops used through PointnetSAModuleMSG: detector/model.py:39-43,64;
+ *  detector/roi_grid_pool.py:28-32,68)
+ * ------------------------------------------------------------------------------------------- */
+V3D_API size_t v3d_fps_workspace_bytes(int B, int N);
+V3D_API int v3d_fps(const float* xyz, int B, int N, int m, int* idx, void* workspace,
+                    size_t workspace_bytes, v3d_stream_t stream);
+V3D_API int v3d_gather(const float* feat, const int* idx, int B, int C, int N, int m, float* out,
+                       v3d_stream_t stream);
+V3D_API int v3d_ball_query(const float* xyz, const float* new_xyz, int B, int N, int M, float radius,
+                           int nsample, int* idx, v3d_stream_t stream);
+V3D_API int v3d_group(const float* feat, const int* idx, int B, int C, int N, int M, int nsample,
+                      float* out, v3d_stream_t stream);
+V3D_API int v3d_query_and_group(const float* xyz, const float* new_xyz, const float* feat,
+                                const int* idx, int B, int C, int N, int M, int nsample, float* out,
+                                v3d_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* V3D_B200_H_ */

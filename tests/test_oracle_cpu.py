@@ -1,0 +1,225 @@
+"""CPU suite (-m "not gpu"): the oracle against the reference's golden vectors / known answers, the
+oracle's internal consistency, and the C-ABI surface. No GPU compute."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CASES = ["known", "spread", "cluster", "degenerate", "offset"]
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_iou_oracle_matches_reference_golden(golden, case):
+    b = golden[case + "_boxes"]
+    # variant 0 == the reference's compiled CPU op, bit for bit; variant 1 == header as nvcc sees it
+    assert np.array_equal(_bits(oracle.box_iou_rotated(b, b, 0)), _bits(golden[case + "_iou_host"]))
+    assert np.array_equal(_bits(oracle.box_iou_rotated(b, b, 1)), _bits(golden[case + "_iou_nvcc"]))
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("thr", [0.01, 0.1, 0.5])
+def test_nms_oracle_matches_reference_golden(golden, case, thr):
+    b, s = golden[case + "_boxes"], golden[case + "_scores"]
+    tag = "%s_%03d" % (case, int(thr * 100))
+    assert np.array_equal(oracle.nms_rotated(b, s, thr, 0), golden["keep_host_" + tag])
+    assert np.array_equal(oracle.nms_rotated(b, s, thr, 1), golden["keep_nvcc_" + tag])
+
+
+def test_known_answers():
+    # SURVEY.md section 4, verified with the reference's own CPU build
+    b = np.array([[0, 0, 2, 2, 0], [1, 1, 2, 2, 0], [0, 0, 2, 2, 45], [10, 10, 2, 2, 0]], np.float32)
+    for v in (0, 1):
+        iou = oracle.box_iou_rotated(b[:1], b, v)[0]
+        assert iou[0] == 1.0 and iou[3] == 0.0
+        assert abs(iou[1] - 1.0 / 7.0) < 1e-6
+        assert abs(iou[2] - 0.70710678) < 1e-6
+        keep = oracle.nms_rotated(b, np.array([.9, .8, .7, .6], np.float32), 0.1, v)
+        assert keep.tolist() == [0, 3]
+
+
+@pytest.mark.skipif(not oracle.ref_available("libref_iou_host.so"), reason="oracle/_ref not built")
+def test_oracle_vs_compiled_reference_random():
+    rng = np.random.default_rng(11)
+    n = 300
+    b = np.stack([rng.uniform(0, 12, n), rng.uniform(-6, 6, n), rng.uniform(0.3, 3, n), rng.uniform(0.3, 5, n),
+                  rng.uniform(-360, 360, n)], 1).astype(np.float32)
+    s = rng.random(n).astype(np.float32)
+    assert np.array_equal(_bits(oracle.box_iou_rotated(b, b, 0)), _bits(oracle.ref_shim_iou(b, b, False)))
+    assert np.array_equal(_bits(oracle.box_iou_rotated(b, b, 1)), _bits(oracle.ref_shim_iou(b, b, True)))
+    for thr in (0.01, 0.3):
+        assert np.array_equal(oracle.nms_rotated(b, s, thr, 0), oracle.ref_shim_nms(b, s, thr, False))
+        assert np.array_equal(oracle.nms_rotated(b, s, thr, 1), oracle.ref_shim_nms(b, s, thr, True))
+
+
+# ---- voxelize: oracle == python dict loop (the documented upstream algorithm) ----------------------
+def _voxelize_py(points, vsize, bounds, max_pts, max_voxels, policy):
+    lo = np.asarray(bounds[:3], np.float32)
+    vs = np.asarray(vsize, np.float32)
+    grid = oracle.grid_size(vsize, bounds)
+    table, vox, coords = {}, [], []
+    for p in points:
+        c = np.floor((p[:3] - lo) / vs)
+        if np.any(c < 0) or np.any(c >= grid):
+            continue
+        key = tuple(int(v) for v in c[::-1])
+        if key not in table:
+            if len(vox) >= max_voxels:
+                if policy == 0:
+                    break
+                continue
+            table[key] = len(vox)
+            vox.append([])
+            coords.append(key)
+        if len(vox[table[key]]) < max_pts:
+            vox[table[key]].append(p)
+    return vox, np.array(coords, np.int32).reshape(-1, 3)
+
+
+@pytest.mark.parametrize("policy", [0, 1])
+def test_voxelize_oracle_vs_python(policy):
+    from vision3d_b200 import synth
+    pts = synth.make_cloud(3, 4000)
+    pts[:50, 0] = -5.0  # out of range
+    for max_voxels in (20000, 700):
+        v, c, n = oracle.voxelize(pts, synth.VOXEL_SIZE, synth.GRID_BOUNDS, 5, max_voxels, policy)
+        pv, pc = _voxelize_py(pts, synth.VOXEL_SIZE, synth.GRID_BOUNDS, 5, max_voxels, policy)
+        assert len(pv) == len(v) and np.array_equal(pc, c)
+        for i, plist in enumerate(pv):
+            assert n[i] == len(plist)
+            assert np.array_equal(v[i, :len(plist)], np.array(plist, np.float32))
+            assert not v[i, len(plist):].any()
+
+
+# ---- sparse conv oracle == dense torch conv3d (independent check that needs no spconv) ------------
+def _dense_conv_check(subm):
+    import torch
+    import torch.nn.functional as F
+    from vision3d_b200 import synth
+    rng = np.random.default_rng(5)
+    shape, B, cin, cout = [9, 14, 12], 2, 4, 8
+    idx = synth.make_active_sites(1, 150, shape, B)
+    feat = rng.normal(size=(len(idx), cin)).astype(np.float32)
+    if subm:
+        w = rng.normal(size=(3, 3, 3, cin, cout)).astype(np.float32)
+        nbr = oracle.rulebook_subm(idx, shape, 3)
+        out_idx, oshape = idx, shape
+        kw = dict(padding=1)
+    else:
+        w = rng.normal(size=(3, 3, 3, cin, cout)).astype(np.float32)
+        out_idx, nbr, oshape = oracle.rulebook_conv(idx, shape, 3, 2, [0, 1, 1])
+        kw = dict(stride=2, padding=(0, 1, 1))
+    out = oracle.sparse_conv(feat, w, nbr)
+    dense_in = torch.from_numpy(oracle.dense(feat, idx, B, shape))
+    wt = torch.from_numpy(w).permute(4, 3, 0, 1, 2).contiguous()
+    ref = F.conv3d(dense_in.double(), wt.double(), **kw).float().numpy()
+    assert list(ref.shape[2:]) == list(oshape)
+    got = oracle.dense(out, out_idx, B, oshape)
+    if subm:
+        mask = oracle.dense(np.ones((len(idx), 1), np.float32), idx, B, shape) > 0
+        ref = ref * mask
+    else:
+        # strided: every touched site is an output; untouched sites are exactly zero in both
+        touched = oracle.dense(np.ones((len(out_idx), 1), np.float32), out_idx, B, oshape) > 0
+        assert np.all((np.abs(ref).sum(1, keepdims=True) > 0) <= touched)
+        flat = ((out_idx[:, 0] * oshape[0] + out_idx[:, 1]) * oshape[1] + out_idx[:, 2]) * oshape[2] + out_idx[:, 3]
+        assert np.all(np.diff(flat) > 0), "strided outputs must be in ascending flat (b,z,y,x) order"
+    np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-5)
+
+
+def test_subm_oracle_vs_dense_conv3d():
+    _dense_conv_check(True)
+
+
+def test_strided_oracle_vs_dense_conv3d():
+    _dense_conv_check(False)
+
+
+def test_second_level_shapes():
+    # detector/sparse_cnn.py:49-56 docstring: 41 -> 21 -> 11 -> 5 -> 2
+    s = [41, 1600, 1408]
+    idx = np.array([[0, 0, 0, 0]], np.int32)
+    for ks, st, pd, want in [(3, 2, 1, [21, 800, 704]), (3, 2, 1, [11, 400, 352]),
+                             (3, 2, [0, 1, 1], [5, 200, 176]), ([3, 1, 1], [2, 1, 1], 0, [2, 200, 176])]:
+        _, _, s = oracle.rulebook_conv(idx, s, ks, st, pd)
+        assert s == want
+
+
+# ---- point ops: oracle == brute-force numpy ---------------------------------------------------------
+def test_fps_oracle_vs_numpy():
+    rng = np.random.default_rng(2)
+    xyz = rng.normal(size=(2, 257, 3)).astype(np.float32)
+    xyz[0, 200:] = xyz[0, :57]  # duplicated points -> exact ties (batch padding duplicates points)
+    got = oracle.fps(xyz, 40)
+    for b in range(2):
+        mind = np.full(257, 1e10, np.float32)
+        cur, want = 0, [0]
+        for _ in range(39):
+            d = xyz[b] - xyz[b, cur]
+            dist = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+            mind = np.minimum(mind, dist.astype(np.float32))
+            cur = int(np.argmax(mind))  # first maximum = lowest index
+            want.append(cur)
+        assert got[b].tolist() == want
+
+
+def test_ball_query_group_oracle_vs_numpy():
+    rng = np.random.default_rng(4)
+    xyz = rng.uniform(-1, 1, size=(2, 300, 3)).astype(np.float32)
+    q = rng.uniform(-1, 1, size=(2, 17, 3)).astype(np.float32)
+    q[0, 0] = 50.0  # no neighbour at all -> zeros
+    idx = oracle.ball_query(0.4, 8, xyz, q)
+    for b in range(2):
+        for j in range(17):
+            d = xyz[b] - q[b, j]
+            hits = np.nonzero(((d[:, 0] ** 2 + d[:, 1] ** 2) + d[:, 2] ** 2).astype(np.float32) < np.float32(0.4) ** 2)[0]
+            want = np.zeros(8, np.int32)
+            if len(hits):
+                want[:] = hits[0]
+                want[:min(8, len(hits))] = hits[:8]
+            assert idx[b, j].tolist() == want.tolist()
+    feat = rng.normal(size=(2, 5, 300)).astype(np.float32)
+    g = oracle.group(feat, idx)
+    assert np.array_equal(g[1, 3, 9], feat[1, 3, idx[1, 9]])
+    qg = oracle.query_and_group(xyz, q, feat, idx)
+    assert qg.shape == (2, 8, 17, 8)
+    assert np.array_equal(qg[0, :3, 5, 2], xyz[0, idx[0, 5, 2]] - q[0, 5])
+    assert np.array_equal(qg[:, 3:], g)
+    assert np.array_equal(oracle.gather(feat, idx[:, :, 0]), feat[np.arange(2)[:, None, None], np.arange(5)[None, :, None], idx[:, None, :, 0]])
+
+
+# ---- the C-ABI surface: library loads and exports every symbol the header declares ----------------
+def test_cabi_library_exports_every_declared_symbol():
+    from vision3d_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "v3d_b200.h")).read()
+    declared = set(re.findall(r"V3D_API [^;]*?(v3d_\w+)\(", hdr))
+    assert declared, "header parse failed"
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.v3d_abi_version() == 1
+    assert lib.v3d_status_string(0) == b"ok"
+    assert lib.v3d_cudart_version() >= 12000
+    # size queries are pure host arithmetic
+    assert lib.v3d_nms_rotated_workspace_bytes(1600) >= 1600 * 25 * 8
+    assert lib.v3d_voxelize_workspace_bytes(16384 * 16, 16) > 0
+
+
+def test_ops_reject_cpu_tensors():
+    import torch
+    from vision3d_b200 import ops
+    from vision3d_b200._lib import V3DError
+    with pytest.raises(V3DError):
+        ops.box_iou_rotated(torch.zeros(2, 5), torch.zeros(3, 5))
+    with pytest.raises(V3DError):
+        ops.nms_rotated(torch.zeros(2, 5), torch.zeros(2), 0.1)
+    with pytest.raises(V3DError):
+        ops.furthest_point_sample(torch.zeros(1, 8, 3), 4)

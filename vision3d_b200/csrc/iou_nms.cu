@@ -1,0 +1,428 @@
+// Rotated BEV IoU (a13/a14) and rotated NMS (a12) for sm_100a.
+//
+// Replaces vision3d/ops/csrc/box_iou_rotated/box_iou_rotated_cuda.cu:14-121 and
+// vision3d/ops/csrc/nms_rotated/nms_rotated_cuda.cu:14-134 (reference tree). Arithmetic follows
+// box_iou_rotated_utils.h:56-340 as nvcc compiles it (exchange-sort hull, :197-214), operation by
+// operation, with fp64 kept at the sites the reference evaluates in fp64 (:61-63, :97, :283,
+// :318-319). THIS FILE IS COMPILED WITH -fmad=false so that no multiply-add is fused: results
+// are bit-identical to oracle variant 1 (the same header built on the host).
+//
+// What is different from the reference kernels (design, not arithmetic):
+//   * per-box work (fp64 sin/cos, the four half-extent products, area, bounding radius) is done
+//     once per box, not once per pair;
+//   * an exact disjointness pre-test (centre distance vs sum of bounding radii, 5 % margin)
+//     short-circuits pairs whose IoU the reference would compute as exactly 0 -- with the
+//     wrapper's per-group coordinate offsets (ops/iou_nms.py:124-132) that is almost every pair;
+//   * NMS never leaves the device: O(N^2) counting rank instead of sort+index_select, only the
+//     upper-triangular 64x64 mask tiles, and a chunked greedy scan replacing the reference's
+//     blocking D2H copy + serial host loop (nms_rotated_cuda.cu:106-128).
+#include "common.cuh"
+
+namespace v3d {
+namespace {
+
+struct V2 {
+  float x, y;
+};
+__device__ __forceinline__ V2 vsub(V2 a, V2 b) { return V2{a.x - b.x, a.y - b.y}; }
+__device__ __forceinline__ float vdot(V2 a, V2 b) { return a.x * b.x + a.y * b.y; }
+__device__ __forceinline__ float vcross(V2 a, V2 b) { return a.x * b.y - b.x * a.y; }
+
+// Per-box invariants of get_rotated_vertices (utils.h:56-74) and single_box_iou_rotated (:329-330).
+struct alignas(16) BoxPre {
+  float x, y, w, h;      // raw centre / size
+  float sh, cw, ch, sw;  // (sin/2)*h, (cos/2)*w, (cos/2)*h, (sin/2)*w
+  float area, rad, pad0, pad1;
+};
+
+__device__ __forceinline__ BoxPre make_pre(const float* __restrict__ b) {
+  BoxPre p;
+  p.x = b[0];
+  p.y = b[1];
+  p.w = b[2];
+  p.h = b[3];
+  double theta = b[4] * 0.01745329251;  // utils.h:61 (fp64)
+  float c2 = (float)cos(theta) * 0.5f;  // :62
+  float s2 = (float)sin(theta) * 0.5f;  // :63
+  p.sh = s2 * p.h;
+  p.cw = c2 * p.w;
+  p.ch = c2 * p.h;
+  p.sw = s2 * p.w;
+  p.area = p.w * p.h;
+  p.rad = 0.5f * sqrtf(p.w * p.w + p.h * p.h);
+  p.pad0 = p.pad1 = 0.f;
+  return p;
+}
+
+__device__ __forceinline__ void corners(float cx, float cy, const BoxPre& b, V2 (&o)[4]) {
+  o[0].x = cx - b.sh - b.cw;
+  o[0].y = cy + b.ch - b.sw;
+  o[1].x = cx + b.sh - b.cw;
+  o[1].y = cy - b.ch - b.sw;
+  o[2].x = 2 * cx - o[0].x;
+  o[2].y = 2 * cy - o[0].y;
+  o[3].x = 2 * cx - o[1].x;
+  o[3].y = 2 * cy - o[1].y;
+}
+
+// true  => the reference computes exactly 0 for this pair (no edge crossing, no contained corner)
+__device__ __forceinline__ bool surely_disjoint(const BoxPre& a, const BoxPre& b) {
+  float dx = a.x - b.x, dy = a.y - b.y;
+  float rr = a.rad + b.rad;
+  return dx * dx + dy * dy > rr * rr * 1.05f;  // NaN/inf anywhere -> false -> full evaluation
+}
+
+__device__ __noinline__ float iou_full(const BoxPre& A, const BoxPre& B) {
+  // utils.h:318-321: centre shift in fp64, rounded to fp32 when stored in the RotatedBox
+  double sx = (A.x + B.x) / 2.0;
+  double sy = (A.y + B.y) / 2.0;
+  float ax = (float)(A.x - sx), ay = (float)(A.y - sy);
+  float bx = (float)(B.x - sx), by = (float)(B.y - sy);
+  if ((double)A.area < 1e-14 || (double)B.area < 1e-14) return 0.f;  // :331-333
+
+  V2 p1[4], p2[4];
+  corners(ax, ay, A, p1);
+  corners(bx, by, B, p2);
+
+  // ---- get_intersection_points, utils.h:76-155 ----
+  V2 pts[24];
+  int n = 0;
+  V2 e1[4], e2[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    e1[i] = vsub(p1[(i + 1) & 3], p1[i]);
+    e2[i] = vsub(p2[(i + 1) & 3], p2[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      float det = vcross(e2[j], e1[i]);
+      if (fabs((double)det) <= 1e-14) continue;
+      V2 d = vsub(p2[j], p1[i]);
+      float t1 = vcross(e2[j], d) / det;
+      float t2 = vcross(e1[i], d) / det;
+      if (t1 >= 0.0f && t1 <= 1.0f && t2 >= 0.0f && t2 <= 1.0f) {
+        pts[n].x = p1[i].x + e1[i].x * t1;
+        pts[n].y = p1[i].y + e1[i].y * t1;
+        n++;
+      }
+    }
+  }
+  {
+    const V2 AB = e2[0], DA = e2[3];
+    const float ABAB = vdot(AB, AB), ADAD = vdot(DA, DA);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      V2 AP = vsub(p1[i], p2[0]);
+      float pAB = vdot(AP, AB);
+      float pAD = -vdot(AP, DA);
+      if (pAB >= 0 && pAD >= 0 && pAB <= ABAB && pAD <= ADAD) pts[n++] = p1[i];
+    }
+  }
+  {
+    const V2 AB = e1[0], DA = e1[3];
+    const float ABAB = vdot(AB, AB), ADAD = vdot(DA, DA);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      V2 AP = vsub(p2[i], p1[0]);
+      float pAB = vdot(AP, AB);
+      float pAD = -vdot(AP, DA);
+      if (pAB >= 0 && pAD >= 0 && pAB <= ABAB && pAD <= ADAD) pts[n++] = p2[i];
+    }
+  }
+
+  float inter = 0.0f;
+  if (n > 2) {  // utils.h:301-303
+    // ---- convex_hull_graham(shift_to_zero = true), utils.h:157-270, nvcc branch ----
+    int t = 0;
+    for (int i = 1; i < n; i++)
+      if (pts[i].y < pts[t].y || (pts[i].y == pts[t].y && pts[i].x < pts[t].x)) t = i;
+    const V2 org = pts[t];
+    V2 q[24];
+    float dist[24];
+    for (int i = 0; i < n; i++) q[i] = vsub(pts[i], org);
+    {
+      V2 tmp = q[0];
+      q[0] = q[t];
+      q[t] = tmp;
+    }
+    for (int i = 0; i < n; i++) dist[i] = vdot(q[i], q[i]);
+    for (int i = 1; i < n - 1; i++) {
+      for (int j = i + 1; j < n; j++) {
+        float cp = vcross(q[i], q[j]);
+        if (((double)cp < -1e-6) || (fabs((double)cp) < 1e-6 && dist[i] > dist[j])) {
+          V2 tq = q[i];
+          q[i] = q[j];
+          q[j] = tq;
+          float td = dist[i];
+          dist[i] = dist[j];
+          dist[j] = td;
+        }
+      }
+    }
+    int k;
+    for (k = 1; k < n; k++)
+      if ((double)dist[k] > 1e-8) break;
+    int m;
+    if (k == n) {
+      m = 1;
+    } else {
+      q[1] = q[k];
+      m = 2;
+      for (int i = k + 1; i < n; i++) {
+        while (m > 1 && vcross(vsub(q[i], q[m - 2]), vsub(q[m - 1], q[m - 2])) >= 0) m--;
+        q[m++] = q[i];
+      }
+    }
+    // ---- polygon_area, utils.h:272-284 ----
+    if (m > 2) {
+      float area = 0;
+      for (int i = 1; i < m - 1; i++) area += fabsf(vcross(vsub(q[i], q[0]), vsub(q[i + 1], q[0])));
+      inter = (float)(area / 2.0);
+    }
+  }
+  return inter / (A.area + B.area - inter);  // utils.h:336
+}
+
+__device__ __forceinline__ float iou_pair(const BoxPre& A, const BoxPre& B) {
+  if (surely_disjoint(A, B)) {
+    // the reference would still return 0 through the area guard or 0/(a1+a2); a1+a2 == 0 cannot
+    // pass the guard, so the value is exactly +0.0f
+    return 0.0f;
+  }
+  return iou_full(A, B);
+}
+
+// -------------------------------------------------------------------------------------------
+// a13: pairwise IoU. Tile = 16 rows x 128 cols, 256 threads, 8 pairs per thread; threads run
+// along the column (contiguous output) dimension.
+// -------------------------------------------------------------------------------------------
+constexpr int kIouTR = 16, kIouTC = 128, kIouThreads = 256;
+
+__global__ void __launch_bounds__(kIouThreads) box_iou_kernel(const float* __restrict__ b1, int M,
+                                                              const float* __restrict__ b2, int N,
+                                                              float* __restrict__ out) {
+  __shared__ BoxPre rows[kIouTR];
+  __shared__ BoxPre cols[kIouTC];
+  const int r0 = blockIdx.y * kIouTR, c0 = blockIdx.x * kIouTC;
+  const int tid = threadIdx.x;
+  if (tid < kIouTC) {
+    if (c0 + tid < N) cols[tid] = make_pre(b2 + (size_t)(c0 + tid) * 5);
+  } else if (tid < kIouTC + kIouTR) {
+    int r = tid - kIouTC;
+    if (r0 + r < M) rows[r] = make_pre(b1 + (size_t)(r0 + r) * 5);
+  }
+  __syncthreads();
+  const int c = tid & (kIouTC - 1);
+  if (c0 + c >= N) return;
+  const BoxPre cb = cols[c];
+#pragma unroll 1
+  for (int r = tid / kIouTC; r < kIouTR; r += kIouThreads / kIouTC) {
+    if (r0 + r >= M) break;
+    out[(size_t)(r0 + r) * N + c0 + c] = iou_pair(rows[r], cb);
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// a12: NMS, three launches.
+// -------------------------------------------------------------------------------------------
+constexpr int kTile = 64;
+
+// (1) counting rank: position of box i in descending-score order, ties -> lower index first.
+//     Also writes the per-box invariants at the sorted position.
+__global__ void __launch_bounds__(256) nms_rank_kernel(const float* __restrict__ dets,
+                                                       const float* __restrict__ scores, int N,
+                                                       int* __restrict__ order,
+                                                       BoxPre* __restrict__ pre) {
+  __shared__ float tile[1024];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float si = 0.f;
+  if (i < N) {
+    si = scores[i];
+    if (si != si) si = __int_as_float(0x7f800000);  // NaN ranks as +inf
+  }
+  int rank = 0;
+  for (int j0 = 0; j0 < N; j0 += 1024) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < 1024; t += blockDim.x) {
+      float s = -__int_as_float(0x7f800000);
+      if (j0 + t < N) {
+        s = scores[j0 + t];
+        if (s != s) s = __int_as_float(0x7f800000);
+      }
+      tile[t] = s;
+    }
+    __syncthreads();
+    if (i < N) {
+      const int lim = min(1024, N - j0);
+      for (int t = 0; t < lim; t++) {
+        float sj = tile[t];
+        rank += (sj > si) || (sj == si && (j0 + t) < i);
+      }
+    }
+  }
+  if (i < N) {
+    order[rank] = i;
+    pre[rank] = make_pre(dets + (size_t)i * 5);
+  }
+}
+
+// (2) upper-triangular mask tiles. Block = 256 threads = 8 warps; warp w owns rows w*8..w*8+7 of
+//     the 64-row tile, lanes cover columns lane and lane+32; __ballot_sync assembles the words.
+__global__ void __launch_bounds__(256) nms_mask_kernel(const BoxPre* __restrict__ pre, int N, float thr,
+                                                       int col_blocks,
+                                                       unsigned long long* __restrict__ mask) {
+  const int rb = blockIdx.y, cb = blockIdx.x;
+  if (cb < rb) return;  // lower triangle is never read by the scan
+  __shared__ BoxPre rbox[kTile];
+  __shared__ BoxPre cbox[kTile];
+  const int tid = threadIdx.x;
+  if (tid < kTile) {
+    if (rb * kTile + tid < N) rbox[tid] = pre[rb * kTile + tid];
+  } else if (tid < 2 * kTile) {
+    int t = tid - kTile;
+    if (cb * kTile + t < N) cbox[t] = pre[cb * kTile + t];
+  }
+  __syncthreads();
+  const int lane = tid & 31, warp = tid >> 5;
+  const int ncol = min(kTile, N - cb * kTile);
+#pragma unroll 1
+  for (int rr = 0; rr < 8; rr++) {
+    const int r = warp * 8 + rr;
+    const int gi = rb * kTile + r;
+    if (gi >= N) break;  // warp-uniform
+    const BoxPre a = rbox[r];
+    unsigned int w[2];
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+      const int c = lane + 32 * half;
+      bool hit = false;
+      if (c < ncol && (rb != cb || c > r)) hit = iou_pair(a, cbox[c]) > thr;  // nms_rotated_cuda.cu:62-63
+      w[half] = __ballot_sync(0xffffffffu, hit);
+    }
+    if (lane == 0)
+      mask[(size_t)gi * col_blocks + cb] = ((unsigned long long)w[1] << 32) | (unsigned long long)w[0];
+  }
+}
+
+// (3) greedy scan (nms_rotated_cuda.cu:115-128) on the device: one block, one thread per mask word.
+//     Per 64-row chunk: thread 0 resolves the chunk against its diagonal word (64 dependent steps
+//     on registers/smem), then every thread ORs the kept rows' words into its removed-word.
+__global__ void __launch_bounds__(1024) nms_scan_kernel(const unsigned long long* __restrict__ mask,
+                                                        const int* __restrict__ order, int N,
+                                                        int col_blocks, long long* __restrict__ keep,
+                                                        int* __restrict__ num_keep) {
+  extern __shared__ unsigned long long remv[];  // col_blocks words
+  __shared__ unsigned long long diag[2][kTile];
+  __shared__ unsigned long long kept_bits;
+  __shared__ int kept_base;
+  const int tid = threadIdx.x;
+  for (int j = tid; j < col_blocks; j += blockDim.x) remv[j] = 0ull;
+  if (tid == 0) kept_base = 0;
+  if (tid < kTile && tid < N) diag[0][tid] = mask[(size_t)tid * col_blocks];
+  __syncthreads();
+  for (int b = 0; b < col_blocks; b++) {
+    const int rows = min(kTile, N - b * kTile);
+    const int cur = b & 1;
+    // prefetch next chunk's diagonal words while this chunk is resolved
+    if (tid >= 64 && tid < 64 + kTile && b + 1 < col_blocks) {
+      int r = (b + 1) * kTile + (tid - 64);
+      if (r < N) diag[cur ^ 1][tid - 64] = mask[(size_t)r * col_blocks + (b + 1)];
+    }
+    if (tid == 0) {
+      unsigned long long removed = remv[b], kept = 0ull;
+      for (int i = 0; i < rows; i++) {
+        if (!((removed >> i) & 1ull)) {
+          kept |= 1ull << i;
+          removed |= diag[cur][i];
+        }
+      }
+      kept_bits = kept;
+    }
+    __syncthreads();
+    const unsigned long long kept = kept_bits;
+    const int base = kept_base;
+    // emit kept indices in order
+    if (tid < rows && ((kept >> tid) & 1ull)) {
+      int pos = base + __popcll(kept & ((1ull << tid) - 1ull));
+      keep[pos] = (long long)order[b * kTile + tid];
+    }
+    // suppress: OR rows of kept boxes into later words
+    for (int j = b + 1 + tid; j < col_blocks; j += blockDim.x) {
+      unsigned long long acc = remv[j];
+      unsigned long long k = kept;
+      while (k) {
+        int i = __ffsll((long long)k) - 1;
+        k &= k - 1;
+        acc |= mask[(size_t)(b * kTile + i) * col_blocks + j];
+      }
+      remv[j] = acc;
+    }
+    __syncthreads();
+    if (tid == 0) kept_base = base + __popcll(kept);
+    __syncthreads();
+  }
+  if (tid == 0) *num_keep = kept_base;
+}
+
+struct NmsLayout {
+  size_t order_off, pre_off, mask_off, total;
+};
+inline NmsLayout nms_layout(int N) {
+  NmsLayout l;
+  size_t cb = (size_t)ceil_div(N, kTile);
+  l.order_off = 0;
+  l.pre_off = align_up(l.order_off + sizeof(int) * (size_t)N, 256);
+  l.mask_off = align_up(l.pre_off + sizeof(BoxPre) * (size_t)N, 256);
+  l.total = align_up(l.mask_off + sizeof(unsigned long long) * (size_t)N * cb, 256);
+  return l;
+}
+
+}  // namespace
+}  // namespace v3d
+
+using namespace v3d;
+
+extern "C" int v3d_box_iou_rotated(const float* boxes1, int M, const float* boxes2, int N, float* ious,
+                                   v3d_stream_t stream) {
+  if (M < 0 || N < 0) return V3D_ERR_INVALID_ARGUMENT;
+  if (M == 0 || N == 0) return V3D_OK;  // box_iou_rotated_cuda.cu:80
+  if (!boxes1 || !boxes2 || !ious) return V3D_ERR_INVALID_ARGUMENT;
+  dim3 grid(ceil_div(N, kIouTC), ceil_div(M, kIouTR));
+  if (grid.y > 65535) return V3D_ERR_INVALID_ARGUMENT;  // cf. box_iou_rotated_cuda.cu:84-95
+  box_iou_kernel<<<grid, kIouThreads, 0, as_stream(stream)>>>(boxes1, M, boxes2, N, ious);
+  return check_launch();
+}
+
+extern "C" size_t v3d_nms_rotated_workspace_bytes(int N) {
+  if (N <= 0) return 256;
+  return nms_layout(N).total;
+}
+
+extern "C" int v3d_nms_rotated(const float* dets, const float* scores, int N, float iou_threshold,
+                               int64_t* keep, int* num_keep, void* workspace, size_t workspace_bytes,
+                               v3d_stream_t stream) {
+  if (N < 0 || !num_keep) return V3D_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = as_stream(stream);
+  if (N == 0) {  // nms_rotated_cpu.cpp:21-23: empty in, empty out
+    V3D_CUDA_TRY(cudaMemsetAsync(num_keep, 0, sizeof(int), st));
+    return V3D_OK;
+  }
+  if (!dets || !scores || !keep || !workspace) return V3D_ERR_INVALID_ARGUMENT;
+  if (N > 65536) return V3D_ERR_INVALID_ARGUMENT;  // one scan thread per mask word, <=1024 words
+  NmsLayout l = nms_layout(N);
+  if (workspace_bytes < l.total) return V3D_ERR_WORKSPACE_TOO_SMALL;
+  char* ws = static_cast<char*>(workspace);
+  int* order = reinterpret_cast<int*>(ws + l.order_off);
+  BoxPre* pre = reinterpret_cast<BoxPre*>(ws + l.pre_off);
+  unsigned long long* mask = reinterpret_cast<unsigned long long*>(ws + l.mask_off);
+  const int cb = ceil_div(N, kTile);
+
+  nms_rank_kernel<<<ceil_div(N, 256), 256, 0, st>>>(dets, scores, N, order, pre);
+  nms_mask_kernel<<<dim3(cb, cb), 256, 0, st>>>(pre, N, iou_threshold, cb, mask);
+  int scan_threads = cb <= 128 ? 128 : (cb <= 256 ? 256 : (cb <= 512 ? 512 : 1024));
+  nms_scan_kernel<<<1, scan_threads, sizeof(unsigned long long) * cb, st>>>(
+      mask, order, N, cb, reinterpret_cast<long long*>(keep), num_keep);
+  return check_launch();
+}

@@ -1,0 +1,328 @@
+// a4: rule-book construction for SubMConv3d / SparseConv3d (spconv get_indice_pairs; layers built at
+// vision3d/detector/sparse_cnn.py:15-30,151-175) on sm_100a.
+//
+// Output-stationary rule table: nbr[kk*stride + o] = input row that feeds output row o through
+// kernel offset kk (or -1). This is the transpose of upstream's per-offset (in,out) pair lists and
+// is what lets the convolution accumulate every offset of an output tile in TMEM/registers and
+// write each output row exactly once (no atomics, no zero-init, BN+ReLU fused in the epilogue).
+//
+// Site table  : epoch-tagged hash (common.cuh) of flat (b,z,y,x) -> row, one per resolution level.
+// SubM        : one lookup per (output row, offset).
+// Strided conv: candidates (in row, offset) mark a bitmap over the output grid; two-level popcount
+//               prefix gives every marked cell its rank in ascending flat order = its output row;
+//               then the same lookup kernel fills nbr from the INPUT level's site table.
+// All counts stay on the device (n_rows / n_out are device ints): no host synchronisation.
+#include "common.cuh"
+
+namespace v3d {
+namespace {
+
+struct TableHeader {
+  unsigned int epoch;
+  unsigned int pad[63];
+};
+
+struct SiteTable {
+  TableHeader* hdr;
+  unsigned long long* keys;
+  int* vals;
+  unsigned int cap;
+  size_t total;
+};
+
+inline SiteTable table_layout(void* base, int capacity_rows) {
+  SiteTable t;
+  char* p = static_cast<char*>(base);
+  t.cap = next_pow2((unsigned int)(2 * (size_t)(capacity_rows > 512 ? capacity_rows : 512)));
+  size_t off = 0;
+  t.hdr = reinterpret_cast<TableHeader*>(p + off);
+  off = align_up(off + sizeof(TableHeader), 256);
+  t.keys = reinterpret_cast<unsigned long long*>(p + off);
+  off = align_up(off + 8ull * t.cap, 256);
+  t.vals = reinterpret_cast<int*>(p + off);
+  off = align_up(off + 4ull * t.cap, 256);
+  t.total = off;
+  return t;
+}
+
+struct Shape3 {
+  int d[3];
+};
+
+__device__ __forceinline__ unsigned long long flat_key(int b, int z, int y, int x, const Shape3& s) {
+  return (((unsigned long long)b * s.d[0] + z) * s.d[1] + y) * (unsigned long long)s.d[2] + x;
+}
+
+__global__ void table_bump_kernel(TableHeader* hdr) { hdr->epoch += 1; }
+
+__global__ void __launch_bounds__(256) table_build_kernel(SiteTable T, const int4* __restrict__ idx,
+                                                          const int* __restrict__ n_rows, int cap_rows,
+                                                          Shape3 shape) {
+  const int n = min(*n_rows, cap_rows);
+  const unsigned int epoch = T.hdr->epoch;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int4 c = idx[i];
+    unsigned int s = table_claim(T.keys, T.cap - 1, epoch, flat_key(c.x, c.y, c.z, c.w, shape));
+    T.vals[s] = i;
+  }
+}
+
+struct ConvGeom {
+  int ks[3], stride[3], pad[3], dil[3];
+  int in_shape[3], out_shape[3];
+  int KV;
+};
+
+// nbr[kk][o] = row of the input site at out*stride - pad + k*dil (or -1). Used by SubM (out set ==
+// in set, stride 1, pad k/2) and by the strided conv once its output rows are known.
+__global__ void __launch_bounds__(256) rule_lookup_kernel(SiteTable T, const int4* __restrict__ out_idx,
+                                                          const int* __restrict__ n_out, int out_cap,
+                                                          ConvGeom G, int identity_kk,
+                                                          int* __restrict__ nbr, int nbr_stride) {
+  const int n = min(*n_out, out_cap);
+  const int kk = blockIdx.y;
+  const int kx = kk % G.ks[2], ky = (kk / G.ks[2]) % G.ks[1], kz = kk / (G.ks[2] * G.ks[1]);
+  const unsigned int epoch = T.hdr->epoch;
+  Shape3 ish{{G.in_shape[0], G.in_shape[1], G.in_shape[2]}};
+  for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n; o += gridDim.x * blockDim.x) {
+    int r;
+    if (kk == identity_kk) {
+      r = o;
+    } else {
+      int4 c = out_idx[o];
+      const int z = c.y * G.stride[0] - G.pad[0] + kz * G.dil[0];
+      const int y = c.z * G.stride[1] - G.pad[1] + ky * G.dil[1];
+      const int x = c.w * G.stride[2] - G.pad[2] + kx * G.dil[2];
+      r = -1;
+      if (z >= 0 && z < G.in_shape[0] && y >= 0 && y < G.in_shape[1] && x >= 0 && x < G.in_shape[2]) {
+        unsigned int s = table_find(T.keys, T.cap - 1, epoch, flat_key(c.x, z, y, x, ish));
+        if (s != 0xFFFFFFFFu) r = __ldg(&T.vals[s]);
+      }
+    }
+    nbr[(size_t)kk * nbr_stride + o] = r;
+  }
+}
+
+// ---- strided conv: discover output sites --------------------------------------------------------
+constexpr int kCoarse = 1024;  // cells per level-1 counter (32 bitmap words)
+
+struct ConvWs {
+  unsigned int* bitmap;  // cells/32 words
+  int* l1;               // per 1024 cells: count, then exclusive prefix inside its level-2 group
+  int* l2;               // per 1024 l1 entries: count, then exclusive prefix
+  unsigned int* uniq;    // unique marked cells, arbitrary order
+  int* n_uniq;
+  size_t n_words, n_l1, n_l2;
+  size_t zero_bytes;  // prefix of the workspace that must be zeroed per call
+  size_t total;
+};
+
+inline ConvWs conv_layout(void* base, unsigned long long cells, int out_capacity) {
+  ConvWs w;
+  char* p = static_cast<char*>(base);
+  w.n_words = (size_t)((cells + 31) / 32);
+  w.n_l1 = (size_t)((cells + kCoarse - 1) / kCoarse);
+  w.n_l2 = (w.n_l1 + 1023) / 1024;
+  size_t off = 0;
+  w.bitmap = reinterpret_cast<unsigned int*>(p + off);
+  off = align_up(off + 4 * (w.n_l1 * 32), 256);  // whole 32-word groups so R3 can read uint4s
+  w.l1 = reinterpret_cast<int*>(p + off);
+  off = align_up(off + 4 * (w.n_l2 * 1024), 256);
+  w.l2 = reinterpret_cast<int*>(p + off);
+  off = align_up(off + 4 * 1024, 256);
+  w.n_uniq = reinterpret_cast<int*>(p + off);
+  off = align_up(off + 4, 256);
+  w.zero_bytes = off;
+  w.uniq = reinterpret_cast<unsigned int*>(p + off);
+  off = align_up(off + 4ull * (size_t)out_capacity, 256);
+  w.total = off;
+  return w;
+}
+
+__global__ void __launch_bounds__(256) conv_mark_kernel(const int4* __restrict__ idx,
+                                                        const int* __restrict__ n_rows, int cap_rows,
+                                                        ConvGeom G, ConvWs W, int out_capacity) {
+  const int n = min(*n_rows, cap_rows);
+  const int kk = blockIdx.y;
+  const int kx = kk % G.ks[2], ky = (kk / G.ks[2]) % G.ks[1], kz = kk / (G.ks[2] * G.ks[1]);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int4 c = idx[i];
+    int nz = c.y + G.pad[0] - kz * G.dil[0];
+    int ny = c.z + G.pad[1] - ky * G.dil[1];
+    int nx = c.w + G.pad[2] - kx * G.dil[2];
+    if (nz < 0 || ny < 0 || nx < 0) continue;
+    if (nz % G.stride[0] || ny % G.stride[1] || nx % G.stride[2]) continue;
+    int oz = nz / G.stride[0], oy = ny / G.stride[1], ox = nx / G.stride[2];
+    if (oz >= G.out_shape[0] || oy >= G.out_shape[1] || ox >= G.out_shape[2]) continue;
+    unsigned int cell =
+        (unsigned int)((((size_t)c.x * G.out_shape[0] + oz) * G.out_shape[1] + oy) * G.out_shape[2] + ox);
+    unsigned int bit = 1u << (cell & 31);
+    unsigned int old = atomicOr(&W.bitmap[cell >> 5], bit);
+    if (!(old & bit)) {
+      atomicAdd(&W.l1[cell / kCoarse], 1);
+      int u = atomicAdd(W.n_uniq, 1);
+      if (u < out_capacity) W.uniq[u] = cell;
+    }
+  }
+}
+
+// in-place: l1[g*1024 .. +1024) -> exclusive prefix inside group g; l2[g] = group total
+__global__ void __launch_bounds__(1024) conv_scan_l1_kernel(ConvWs W) {
+  __shared__ int sm[33];
+  const size_t i = (size_t)blockIdx.x * 1024 + threadIdx.x;
+  int v = i < W.n_l1 ? W.l1[i] : 0;
+  int total;
+  int ex = block_exclusive_scan(v, sm, total);
+  if (i < W.n_l1) W.l1[i] = ex;
+  if (threadIdx.x == 0) W.l2[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) conv_scan_l2_kernel(ConvWs W, int* __restrict__ n_out) {
+  __shared__ int sm[33];
+  int v = threadIdx.x < W.n_l2 ? W.l2[threadIdx.x] : 0;
+  int total;
+  int ex = block_exclusive_scan(v, sm, total);
+  if (threadIdx.x < W.n_l2) W.l2[threadIdx.x] = ex;
+  if (threadIdx.x == 0) *n_out = total;  // un-clamped: caller detects overflow as n_out > capacity
+}
+
+__global__ void __launch_bounds__(256) conv_rank_kernel(ConvWs W, ConvGeom G, int out_capacity,
+                                                        int4* __restrict__ out_idx) {
+  const int n = min(*W.n_uniq, out_capacity);
+  for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
+    const unsigned int cell = W.uniq[u];
+    const unsigned int g1 = cell / kCoarse;
+    int rank = W.l2[g1 >> 10] + W.l1[g1];
+    const unsigned int w0 = g1 * 32, wq = cell >> 5;
+    for (unsigned int w = w0; w < wq; w++) rank += __popc(__ldg(&W.bitmap[w]));
+    rank += __popc(__ldg(&W.bitmap[wq]) & ((1u << (cell & 31)) - 1u));
+    if (rank < out_capacity) {
+      unsigned int r = cell;
+      int x = r % G.out_shape[2];
+      r /= G.out_shape[2];
+      int y = r % G.out_shape[1];
+      r /= G.out_shape[1];
+      int z = r % G.out_shape[0];
+      r /= G.out_shape[0];
+      out_idx[rank] = make_int4((int)r, z, y, x);
+    }
+  }
+}
+
+inline void fill_geom(ConvGeom& G, const int* shape, const int* ks, const int* stride, const int* pad,
+                      const int* dil) {
+  for (int d = 0; d < 3; d++) {
+    G.ks[d] = ks[d];
+    G.stride[d] = stride[d];
+    G.pad[d] = pad[d];
+    G.dil[d] = dil[d];
+    G.in_shape[d] = shape[d];
+    G.out_shape[d] = (shape[d] + 2 * pad[d] - dil[d] * (ks[d] - 1) - 1) / stride[d] + 1;
+  }
+  G.KV = ks[0] * ks[1] * ks[2];
+}
+
+inline int row_grid(int cap_rows) {
+  int blocks = ceil_div(cap_rows > 0 ? cap_rows : 1, 256);
+  return blocks < kNumSMs * 8 ? blocks : kNumSMs * 8;
+}
+
+}  // namespace
+}  // namespace v3d
+
+using namespace v3d;
+
+extern "C" size_t v3d_site_table_bytes(int capacity_rows) {
+  if (capacity_rows < 0) return 0;
+  return table_layout(nullptr, capacity_rows).total;
+}
+
+extern "C" int v3d_site_table_init(void* table, size_t table_bytes, int capacity_rows, v3d_stream_t stream) {
+  if (!table || capacity_rows < 0) return V3D_ERR_INVALID_ARGUMENT;
+  SiteTable T = table_layout(table, capacity_rows);
+  if (table_bytes < T.total) return V3D_ERR_WORKSPACE_TOO_SMALL;
+  V3D_CUDA_TRY(cudaMemsetAsync(table, 0, T.total, as_stream(stream)));  // epoch 0 = never written
+  return V3D_OK;
+}
+
+extern "C" int v3d_site_table_build(void* table, const int* indices, const int* n_rows, int capacity_rows,
+                                    const int* shape_host, v3d_stream_t stream) {
+  if (!table || !indices || !n_rows || !shape_host || capacity_rows < 0) return V3D_ERR_INVALID_ARGUMENT;
+  SiteTable T = table_layout(table, capacity_rows);
+  Shape3 s{{shape_host[0], shape_host[1], shape_host[2]}};
+  cudaStream_t st = as_stream(stream);
+  table_bump_kernel<<<1, 1, 0, st>>>(T.hdr);
+  table_build_kernel<<<row_grid(capacity_rows), 256, 0, st>>>(T, reinterpret_cast<const int4*>(indices),
+                                                            n_rows, capacity_rows, s);
+  return check_launch();
+}
+
+extern "C" int v3d_rulebook_subm(const void* table, const int* indices, const int* n_rows,
+                                 int capacity_rows, const int* shape_host, const int* ksize_host,
+                                 const int* dilation_host, int* nbr, int nbr_stride, v3d_stream_t stream) {
+  if (!table || !indices || !n_rows || !shape_host || !ksize_host || !dilation_host || !nbr)
+    return V3D_ERR_INVALID_ARGUMENT;
+  if (nbr_stride < capacity_rows) return V3D_ERR_INVALID_ARGUMENT;
+  for (int d = 0; d < 3; d++)
+    if (ksize_host[d] <= 0 || (ksize_host[d] & 1) == 0) return V3D_ERR_INVALID_ARGUMENT;  // SubM: odd
+  SiteTable T = table_layout(const_cast<void*>(table), capacity_rows);
+  ConvGeom G;
+  int one[3] = {1, 1, 1};
+  int pad[3] = {ksize_host[0] / 2 * dilation_host[0], ksize_host[1] / 2 * dilation_host[1],
+                ksize_host[2] / 2 * dilation_host[2]};
+  fill_geom(G, shape_host, ksize_host, one, pad, dilation_host);
+  if (G.KV > 65535) return V3D_ERR_INVALID_ARGUMENT;
+  const int centre = ((ksize_host[0] / 2) * ksize_host[1] + ksize_host[1] / 2) * ksize_host[2] +
+                     ksize_host[2] / 2;
+  dim3 grid(row_grid(capacity_rows), G.KV);
+  rule_lookup_kernel<<<grid, 256, 0, as_stream(stream)>>>(T, reinterpret_cast<const int4*>(indices), n_rows,
+                                                          capacity_rows, G, centre, nbr, nbr_stride);
+  return check_launch();
+}
+
+extern "C" void v3d_conv_out_shape(const int* shape, const int* ksize, const int* stride, const int* pad,
+                                   const int* dilation, int* out_shape) {
+  ConvGeom G;
+  fill_geom(G, shape, ksize, stride, pad, dilation);
+  for (int d = 0; d < 3; d++) out_shape[d] = G.out_shape[d];
+}
+
+extern "C" size_t v3d_rulebook_conv_workspace_bytes(int B, const int* out_shape_host, int capacity_rows,
+                                                    int kernel_volume) {
+  (void)kernel_volume;
+  if (B <= 0 || !out_shape_host || capacity_rows < 0) return 0;
+  unsigned long long cells = (unsigned long long)B * out_shape_host[0] * out_shape_host[1] * out_shape_host[2];
+  return conv_layout(nullptr, cells, capacity_rows).total;
+}
+
+extern "C" int v3d_rulebook_conv(const void* in_table, const int* indices, const int* n_rows,
+                                 int capacity_rows, int B, const int* shape_host, const int* ksize_host,
+                                 const int* stride_host, const int* pad_host, const int* dilation_host,
+                                 int* out_indices, int* n_out, int out_capacity, int* nbr, int nbr_stride,
+                                 void* workspace, size_t workspace_bytes, v3d_stream_t stream) {
+  if (!in_table || !indices || !n_rows || !shape_host || !ksize_host || !stride_host || !pad_host ||
+      !dilation_host || !out_indices || !n_out || !nbr || !workspace)
+    return V3D_ERR_INVALID_ARGUMENT;
+  if (B <= 0 || out_capacity <= 0 || nbr_stride < out_capacity) return V3D_ERR_INVALID_ARGUMENT;
+  ConvGeom G;
+  fill_geom(G, shape_host, ksize_host, stride_host, pad_host, dilation_host);
+  for (int d = 0; d < 3; d++)
+    if (G.out_shape[d] <= 0 || stride_host[d] <= 0) return V3D_ERR_INVALID_ARGUMENT;
+  if (G.KV > 65535) return V3D_ERR_INVALID_ARGUMENT;
+  unsigned long long cells = (unsigned long long)B * G.out_shape[0] * G.out_shape[1] * G.out_shape[2];
+  if (cells >= (1ull << 30)) return V3D_ERR_INVALID_ARGUMENT;  // level-2 scan is one 1024-thread block
+  ConvWs W = conv_layout(workspace, cells, out_capacity);
+  if (workspace_bytes < W.total) return V3D_ERR_WORKSPACE_TOO_SMALL;
+  SiteTable T = table_layout(const_cast<void*>(in_table), capacity_rows);
+  cudaStream_t st = as_stream(stream);
+  V3D_CUDA_TRY(cudaMemsetAsync(workspace, 0, W.zero_bytes, st));
+  conv_mark_kernel<<<dim3(row_grid(capacity_rows), G.KV), 256, 0, st>>>(
+      reinterpret_cast<const int4*>(indices), n_rows, capacity_rows, G, W, out_capacity);
+  conv_scan_l1_kernel<<<(unsigned int)W.n_l2, 1024, 0, st>>>(W);
+  conv_scan_l2_kernel<<<1, 1024, 0, st>>>(W, n_out);
+  conv_rank_kernel<<<row_grid(out_capacity), 256, 0, st>>>(W, G, out_capacity,
+                                                          reinterpret_cast<int4*>(out_indices));
+  rule_lookup_kernel<<<dim3(row_grid(out_capacity), G.KV), 256, 0, st>>>(
+      T, reinterpret_cast<const int4*>(out_indices), n_out, out_capacity, G, -1, nbr, nbr_stride);
+  return check_launch();
+}

@@ -1,0 +1,335 @@
+// a1 (+a2): batched point -> voxel hashing and scatter for sm_100a.
+//
+// Replaces spconv.utils.VoxelGenerator.generate (CPU, one frame at a time, sequential over points,
+// 360 MB dense lookup grid) as called from vision3d/core/preprocess.py:17-33, for ALL frames of a
+// batch in one call, and optionally VoxelFeatureExtractor.forward (detector/layers.py:10-17).
+//
+// The upstream algorithm is sequential (voxel id = order of first appearance, slot = arrival
+// order). It is reproduced exactly and deterministically in parallel:
+//   K1 insert : every point claims the hash slot of its (frame, cell) key, atomicMax's the
+//               (inverted) point index into the slot  -> first point of every cell, and pushes
+//               itself on the slot's linked list.
+//   K2 count  : a point is a "voxel opener" iff it is its cell's first point; openers per 1024-pt
+//               chunk are counted.
+//   K3 assign : voxel id of an opener = number of openers before it in the frame (block scan +
+//               chunk prefix); applies the max_voxels cap (break / continue policy); writes
+//               coords, per-frame voxel offsets (frames packed back to back).
+//   K4 scatter: slot of a point inside its voxel = number of list members with a smaller index
+//               (rank, independent of the order atomics happened to arrive in); the opener also
+//               writes num_points and the zero padding.
+//   K5 mean   : optional fused VFE (sum over slots / count).
+// The hash table is epoch tagged (common.cuh), so nothing is cleared between calls.
+#include <limits.h>
+
+#include "common.cuh"
+
+namespace v3d {
+namespace {
+
+constexpr int kChunk = 1024;
+
+struct VoxHeader {
+  unsigned int epoch;
+  unsigned int pad[63];
+};
+
+struct VoxWs {
+  VoxHeader* hdr;
+  unsigned long long* keys;
+  unsigned long long* firstmax;
+  unsigned long long* head;
+  int* slot_vid;
+  unsigned int* pt_slot;
+  int* pt_next;
+  int* chunk_count;  // [B][cpf_cap]
+  int* frame_cut;    // [B]
+  unsigned int cap;  // slots (power of two)
+  int cpf_cap;       // chunks per frame capacity
+  size_t total;
+};
+
+inline VoxWs vox_layout(void* base, int P, int B) {
+  VoxWs w;
+  char* p = static_cast<char*>(base);
+  size_t off = 0;
+  w.cap = next_pow2((unsigned int)(2 * (size_t)(P > 512 ? P : 512)));
+  w.cpf_cap = ceil_div(P > 1 ? P : 1, kChunk);
+  auto take = [&](size_t bytes) {
+    char* r = p + off;
+    off = align_up(off + bytes, 256);
+    return r;
+  };
+  w.hdr = reinterpret_cast<VoxHeader*>(take(sizeof(VoxHeader)));
+  w.keys = reinterpret_cast<unsigned long long*>(take(8ull * w.cap));
+  w.firstmax = reinterpret_cast<unsigned long long*>(take(8ull * w.cap));
+  w.head = reinterpret_cast<unsigned long long*>(take(8ull * w.cap));
+  w.slot_vid = reinterpret_cast<int*>(take(4ull * w.cap));
+  w.pt_slot = reinterpret_cast<unsigned int*>(take(4ull * (size_t)P));
+  w.pt_next = reinterpret_cast<int*>(take(4ull * (size_t)P));
+  w.chunk_count = reinterpret_cast<int*>(take(4ull * (size_t)B * w.cpf_cap));
+  w.frame_cut = reinterpret_cast<int*>(take(4ull * (size_t)B));
+  w.total = off;
+  return w;
+}
+
+struct VoxParams {
+  float lo[3], vs[3];
+  int grid[3];
+  int C, B, max_pts, max_voxels, cap_policy;
+  unsigned long long cells;  // grid[0]*grid[1]*grid[2]
+};
+
+// cell coordinates of one point; false if outside. Same fp32 arithmetic as the oracle:
+// floor((p - lo) / vs) with IEEE division.
+__device__ __forceinline__ bool point_cell(const float* __restrict__ pt, const VoxParams& P, int (&c)[3]) {
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    float f = floorf(__fdiv_rn(pt[j] - P.lo[j], P.vs[j]));
+    if (!(f >= 0.0f) || !(f < (float)P.grid[j])) return false;
+    c[j] = (int)f;
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(kChunk) vox_insert_kernel(const float* __restrict__ points,
+                                                            const int* __restrict__ frame_off,
+                                                            VoxParams P, VoxWs W) {
+  const int b = blockIdx.y;
+  const int start = frame_off[b], n = frame_off[b + 1] - start;
+  const int il = blockIdx.x * kChunk + threadIdx.x;
+  if (il >= n) return;
+  const size_t g = (size_t)start + il;
+  const unsigned int epoch = W.hdr->epoch;
+  int c[3];
+  float pt[3];
+  pt[0] = points[g * P.C + 0];
+  pt[1] = points[g * P.C + 1];
+  pt[2] = points[g * P.C + 2];
+  if (!point_cell(pt, P, c)) {
+    W.pt_slot[g] = 0xFFFFFFFFu;
+    return;
+  }
+  unsigned long long cell = ((unsigned long long)c[2] * P.grid[1] + c[1]) * P.grid[0] + c[0];
+  unsigned long long key = (unsigned long long)b * P.cells + cell;
+  unsigned int s = table_claim(W.keys, W.cap - 1, epoch, key);
+  const unsigned long long tag = (unsigned long long)epoch << 32;
+  atomicMax(&W.firstmax[s], tag | (unsigned long long)(~(unsigned int)il));
+  unsigned long long old = atomicExch(&W.head[s], tag | (unsigned long long)(unsigned int)il);
+  W.pt_next[g] = ((unsigned int)(old >> 32) == epoch) ? (int)(unsigned int)old : -1;
+  W.pt_slot[g] = s;
+}
+
+__global__ void __launch_bounds__(kChunk) vox_count_kernel(const int* __restrict__ frame_off, VoxWs W) {
+  const int b = blockIdx.y;
+  const int start = frame_off[b], n = frame_off[b + 1] - start;
+  if (blockIdx.x * kChunk >= n && blockIdx.x > 0) return;
+  const int il = blockIdx.x * kChunk + threadIdx.x;
+  int flag = 0;
+  if (il < n) {
+    unsigned int s = W.pt_slot[(size_t)start + il];
+    if (s != 0xFFFFFFFFu) flag = (~(unsigned int)W.firstmax[s]) == (unsigned int)il;
+  }
+  int cnt = __syncthreads_count(flag);
+  if (threadIdx.x == 0) {
+    W.chunk_count[b * W.cpf_cap + blockIdx.x] = cnt;
+    if (blockIdx.x == 0) {
+      W.frame_cut[b] = INT_MAX;
+      if (b == 0) W.hdr->epoch += 1;  // K1 of this call has finished: next call sees a clean table
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kChunk) vox_assign_kernel(const float* __restrict__ points,
+                                                            const int* __restrict__ frame_off,
+                                                            VoxParams P, VoxWs W, int* __restrict__ coords,
+                                                            int* __restrict__ voxel_offsets) {
+  __shared__ int sm_scan[33];
+  __shared__ int sm_frame_base, sm_chunk_prefix;
+  const int b = blockIdx.y;
+  const int start = frame_off[b], n = frame_off[b + 1] - start;
+  if (blockIdx.x * kChunk >= n && blockIdx.x > 0) return;
+  // frame base = sum over earlier frames of min(openers, max_voxels); chunk prefix inside frame
+  if (threadIdx.x < 32) {
+    int base = 0;
+    for (int f = 0; f <= b; f++) {
+      const int nf = frame_off[f + 1] - frame_off[f];
+      const int nch = f < b ? ceil_div(nf, kChunk) : (int)blockIdx.x;
+      int s = 0;
+      for (int cidx = threadIdx.x; cidx < nch; cidx += 32) s += W.chunk_count[f * W.cpf_cap + cidx];
+#pragma unroll
+      for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+      if (f < b) base += min(s, P.max_voxels);
+      else if (threadIdx.x == 0) sm_chunk_prefix = s;
+    }
+    if (threadIdx.x == 0) sm_frame_base = base;
+  }
+  __syncthreads();
+  const int il = blockIdx.x * kChunk + threadIdx.x;
+  const size_t g = (size_t)start + il;
+  int flag = 0;
+  unsigned int s = 0xFFFFFFFFu;
+  if (il < n) {
+    s = W.pt_slot[g];
+    if (s != 0xFFFFFFFFu) flag = (~(unsigned int)W.firstmax[s]) == (unsigned int)il;
+  }
+  int total;
+  const int ex = block_exclusive_scan(flag, sm_scan, total);
+  const int vid_local = sm_chunk_prefix + ex;
+  if (flag) {
+    if (vid_local < P.max_voxels) {
+      const int row = sm_frame_base + vid_local;
+      W.slot_vid[s] = row;
+      int c[3];
+      float pt[3] = {points[g * P.C], points[g * P.C + 1], points[g * P.C + 2]};
+      point_cell(pt, P, c);
+      reinterpret_cast<int4*>(coords)[row] = make_int4(b, c[2], c[1], c[0]);
+    } else {
+      W.slot_vid[s] = -1;
+      if (vid_local == P.max_voxels) W.frame_cut[b] = il;  // the point upstream `break`s on
+    }
+  }
+  // last chunk of the frame publishes the frame's packed row range
+  if (threadIdx.x == 0 && (int)(blockIdx.x + 1) * kChunk >= n) {
+    const int m = min(sm_chunk_prefix + total, P.max_voxels);
+    if (b == 0) voxel_offsets[0] = 0;
+    voxel_offsets[b + 1] = sm_frame_base + m;
+  }
+}
+
+template <bool kVec4>
+__global__ void __launch_bounds__(kChunk) vox_scatter_kernel(const float* __restrict__ points,
+                                                             const int* __restrict__ frame_off,
+                                                             VoxParams P, VoxWs W, float* __restrict__ voxels,
+                                                             int* __restrict__ num_points) {
+  const int b = blockIdx.y;
+  const int start = frame_off[b], n = frame_off[b + 1] - start;
+  const int il = blockIdx.x * kChunk + threadIdx.x;
+  if (il >= n) return;
+  const size_t g = (size_t)start + il;
+  const unsigned int s = W.pt_slot[g];
+  if (s == 0xFFFFFFFFu) return;
+  const int row = W.slot_vid[s];
+  if (row < 0) return;
+  const int cut = P.cap_policy == 0 ? W.frame_cut[b] : INT_MAX;
+  if (il >= cut) return;
+  const bool opener = (~(unsigned int)W.firstmax[s]) == (unsigned int)il;
+  // walk the cell's list: rank = members with a smaller index; the opener also needs the
+  // member count (below the cut) for num_points / zero padding
+  int rank = 0, cnt = 0;
+  int j = (int)(unsigned int)W.head[s];
+  while (j >= 0) {
+    if (j < cut) {
+      cnt++;
+      rank += (j < il);
+    }
+    if (!opener && rank >= P.max_pts) return;
+    j = W.pt_next[(size_t)start + j];
+  }
+  float* vrow = voxels + (size_t)row * P.max_pts * P.C;
+  if (rank < P.max_pts) {
+    if (kVec4) {
+      reinterpret_cast<float4*>(vrow)[rank] = reinterpret_cast<const float4*>(points)[g];
+    } else {
+      for (int c = 0; c < P.C; c++) vrow[rank * P.C + c] = points[g * P.C + c];
+    }
+  }
+  if (opener) {
+    const int k = min(cnt, P.max_pts);
+    num_points[row] = k;
+    if (kVec4) {
+      for (int r = k; r < P.max_pts; r++) reinterpret_cast<float4*>(vrow)[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      for (int e = k * P.C; e < P.max_pts * P.C; e++) vrow[e] = 0.f;
+    }
+  }
+}
+
+// a2: mean over the occupied slots (zero padding makes the sum over all slots equal)
+__global__ void vox_mean_kernel(const float* __restrict__ voxels, const int* __restrict__ num_points,
+                                const int* __restrict__ voxel_offsets, int B, int max_pts, int C,
+                                float* __restrict__ mean) {
+  const int total_rows = voxel_offsets[B];
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total_rows * C) return;
+  const int row = e / C, c = e - row * C;
+  float s = 0.f;
+  for (int k = 0; k < max_pts; k++) s += voxels[((size_t)row * max_pts + k) * C + c];
+  mean[e] = __fdiv_rn(s, (float)num_points[row]);
+}
+
+__global__ void vox_init_kernel(unsigned long long* a, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = 0ull;
+}
+
+}  // namespace
+}  // namespace v3d
+
+using namespace v3d;
+
+extern "C" size_t v3d_voxelize_workspace_bytes(int total_points_capacity, int B) {
+  if (total_points_capacity < 0 || B <= 0) return 0;
+  return vox_layout(nullptr, total_points_capacity, B).total;
+}
+
+extern "C" int v3d_voxelize_workspace_init(void* workspace, size_t workspace_bytes,
+                                           int total_points_capacity, int B, v3d_stream_t stream) {
+  if (!workspace || total_points_capacity < 0 || B <= 0) return V3D_ERR_INVALID_ARGUMENT;
+  VoxWs W = vox_layout(workspace, total_points_capacity, B);
+  if (workspace_bytes < W.total) return V3D_ERR_WORKSPACE_TOO_SMALL;
+  cudaStream_t st = as_stream(stream);
+  // epoch 0 everywhere = "never written"; live epochs start at 1
+  V3D_CUDA_TRY(cudaMemsetAsync(workspace, 0, W.total, st));
+  unsigned int one = 1;
+  V3D_CUDA_TRY(cudaMemcpyAsync(&W.hdr->epoch, &one, sizeof(one), cudaMemcpyHostToDevice, st));
+  V3D_CUDA_TRY(cudaStreamSynchronize(st));  // `one` lives on this stack frame
+  return V3D_OK;
+}
+
+extern "C" int v3d_voxelize_batch(const float* points, int total_points, int max_frame_points, int C,
+                                  const int* frame_offsets, int B, const float* range_min_host, const float* voxel_size_host,
+                                  const int* grid_host, int max_pts, int max_voxels, int cap_policy,
+                                  float* voxels, int* coords, int* num_points, int* voxel_offsets,
+                                  float* mean, void* workspace, size_t workspace_bytes,
+                                  int points_capacity, v3d_stream_t stream) {
+  if (total_points > points_capacity || max_frame_points > total_points || max_frame_points < 0)
+    return V3D_ERR_INVALID_ARGUMENT;
+  if (total_points < 0 || B <= 0 || C < 3 || max_pts <= 0 || max_voxels <= 0) return V3D_ERR_INVALID_ARGUMENT;
+  if (!frame_offsets || !range_min_host || !voxel_size_host || !grid_host || !voxels || !coords ||
+      !num_points || !voxel_offsets || !workspace)
+    return V3D_ERR_INVALID_ARGUMENT;
+  if (total_points > 0 && !points) return V3D_ERR_INVALID_ARGUMENT;
+  VoxParams P;
+  for (int j = 0; j < 3; j++) {
+    P.lo[j] = range_min_host[j];
+    P.vs[j] = voxel_size_host[j];
+    P.grid[j] = grid_host[j];
+    if (grid_host[j] <= 0) return V3D_ERR_INVALID_ARGUMENT;
+  }
+  P.C = C;
+  P.B = B;
+  P.max_pts = max_pts;
+  P.max_voxels = max_voxels;
+  P.cap_policy = cap_policy;
+  P.cells = (unsigned long long)grid_host[0] * grid_host[1] * grid_host[2];
+  if ((long double)P.cells * B >= (long double)(1ull << kKeyBits)) return V3D_ERR_INVALID_ARGUMENT;
+  // the persistent table is addressed with the layout it was initialised with
+  VoxWs W = vox_layout(workspace, points_capacity, B);
+  if (workspace_bytes < W.total) return V3D_ERR_WORKSPACE_TOO_SMALL;
+  cudaStream_t st = as_stream(stream);
+  dim3 grid(ceil_div(max_frame_points > 0 ? max_frame_points : 1, kChunk), B);
+  vox_insert_kernel<<<grid, kChunk, 0, st>>>(points, frame_offsets, P, W);
+  vox_count_kernel<<<grid, kChunk, 0, st>>>(frame_offsets, W);
+  vox_assign_kernel<<<grid, kChunk, 0, st>>>(points, frame_offsets, P, W, coords, voxel_offsets);
+  if (C == 4)
+    vox_scatter_kernel<true><<<grid, kChunk, 0, st>>>(points, frame_offsets, P, W, voxels, num_points);
+  else
+    vox_scatter_kernel<false><<<grid, kChunk, 0, st>>>(points, frame_offsets, P, W, voxels, num_points);
+  if (mean) {
+    const long long rows_cap = (long long)B * max_voxels;
+    const long long elems = rows_cap * C;
+    const int blocks = (int)((elems + 255) / 256);
+    vox_mean_kernel<<<blocks, 256, 0, st>>>(voxels, num_points, voxel_offsets, B, max_pts, C, mean);
+  }
+  return check_launch();
+}

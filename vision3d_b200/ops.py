@@ -1,0 +1,338 @@
+"""Torch-tensor front end of the C-ABI (include/v3d_b200.h). PyTorch is plumbing only: it owns the
+device buffers and the stream; every computation below is a hand-written sm_100a kernel.
+
+Two flavours per op:
+  * `*_padded` / capacity-based calls never synchronise: data-dependent sizes stay in device int32
+    counters, outputs are allocated at a static capacity (CUDA-graph friendly; used by second.py);
+  * the reference-shaped wrappers (same names/arguments/return shapes as the ops the reference
+    imports) read the counter back and slice, like the reference ops do.
+
+CPU tensors are rejected loudly -- there is no CPU path (the reference dispatches on
+`tensor.device().is_cuda()`, box_iou_rotated.h:23-31; here CUDA is the only branch).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import V3DError, check, f3, i3
+
+_I32 = torch.int32
+_F32 = torch.float32
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _cuda_f32(t, name, shape_last=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise V3DError("%s must be a CUDA tensor (vision3d_b200 has no CPU path)" % name)
+    if t.dtype != _F32:
+        t = t.float()
+    if not t.is_contiguous():
+        t = t.contiguous()
+    if shape_last is not None and (t.dim() == 0 or t.shape[-1] != shape_last):
+        raise V3DError("%s must have last dimension %d, got %s" % (name, shape_last, tuple(t.shape)))
+    return t
+
+
+def _cuda_i32(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise V3DError("%s must be a CUDA tensor (vision3d_b200 has no CPU path)" % name)
+    if t.dtype != _I32:
+        t = t.int()
+    if not t.is_contiguous():
+        t = t.contiguous()
+    return t
+
+
+def _triple(v):
+    if isinstance(v, (list, tuple)):
+        assert len(v) == 3
+        return [int(x) for x in v]
+    return [int(v)] * 3
+
+
+# =============================================================================================
+# a13 / a12: rotated IoU + NMS  (vision3d._C.box_iou_rotated / nms_rotated, csrc/vision.cpp:63-64)
+# =============================================================================================
+def box_iou_rotated(boxes1, boxes2):
+    b1 = _cuda_f32(boxes1, "boxes1", 5)
+    b2 = _cuda_f32(boxes2, "boxes2", 5)
+    m, n = b1.shape[0], b2.shape[0]
+    out = torch.empty((m, n), dtype=_F32, device=b1.device)
+    with torch.cuda.device(b1.device):
+        check(_lib.load().v3d_box_iou_rotated(b1.data_ptr(), m, b2.data_ptr(), n, out.data_ptr(), _stream()),
+              "v3d_box_iou_rotated")
+    return out
+
+
+def nms_workspace(n, device):
+    nbytes = _lib.load().v3d_nms_rotated_workspace_bytes(int(n))
+    return torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+
+def nms_rotated_padded(dets, scores, iou_threshold, workspace=None, keep=None, count=None):
+    """No host sync. Returns (keep[N] int64, count[1] int32); keep[:count] is valid."""
+    d = _cuda_f32(dets, "dets", 5)
+    s = _cuda_f32(scores, "scores")
+    n = d.shape[0]
+    if s.numel() != n:
+        raise V3DError("dets and scores disagree on N")
+    if keep is None:
+        keep = torch.empty(max(n, 1), dtype=torch.int64, device=d.device)
+    if count is None:
+        count = torch.zeros(1, dtype=_I32, device=d.device)
+    if workspace is None:
+        workspace = nms_workspace(n, d.device)
+    with torch.cuda.device(d.device):
+        check(_lib.load().v3d_nms_rotated(d.data_ptr(), s.data_ptr(), n, float(iou_threshold), keep.data_ptr(),
+                                          count.data_ptr(), workspace.data_ptr(), workspace.numel(), _stream()),
+              "v3d_nms_rotated")
+    return keep, count
+
+
+def nms_rotated(dets, scores, iou_threshold):
+    """Reference-shaped: int64 indices of kept boxes, descending score (nms_rotated_cuda.cu:131-133)."""
+    if dets.numel() == 0:
+        if not dets.is_cuda:
+            raise V3DError("dets must be a CUDA tensor (vision3d_b200 has no CPU path)")
+        return torch.empty((0,), dtype=torch.int64, device=dets.device)
+    keep, count = nms_rotated_padded(dets, scores, iou_threshold)
+    return keep[: int(count.item())]
+
+
+# =============================================================================================
+# a1 / a2: voxelize
+# =============================================================================================
+class Voxelizer:
+    """Batched point->voxel generator (replaces spconv.utils.VoxelGenerator + the batching loop of
+    vision3d/core/preprocess.py:26-33). Holds the persistent, epoch-tagged hash workspace."""
+
+    def __init__(self, voxel_size, point_cloud_range, max_voxels, max_num_points, batch_capacity,
+                 points_capacity, device="cuda", cap_policy=0):
+        import numpy as np
+        self.voxel_size = np.asarray(voxel_size, dtype=np.float32)
+        self.range = np.asarray(point_cloud_range, dtype=np.float32)
+        # spconv VoxelGenerator: grid = round((hi - lo) / voxel_size) in fp32
+        self.grid = np.round((self.range[3:] - self.range[:3]) / self.voxel_size).astype(np.int64)
+        self.max_voxels, self.max_pts = int(max_voxels), int(max_num_points)
+        self.B, self.P = int(batch_capacity), int(points_capacity)
+        self.cap_policy = int(cap_policy)
+        self.device = torch.device(device)
+        lib = _lib.load()
+        nbytes = lib.v3d_voxelize_workspace_bytes(self.P, self.B)
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self._calls = 0
+        self._init_ws()
+
+    def _init_ws(self):
+        with torch.cuda.device(self.device):
+            check(_lib.load().v3d_voxelize_workspace_init(self.ws.data_ptr(), self.ws.numel(), self.P, self.B,
+                                                          _stream()), "v3d_voxelize_workspace_init")
+        self._calls = 0
+
+    def alloc_outputs(self, C, with_mean=True):
+        rows = self.B * self.max_voxels
+        dev = self.device
+        out = dict(voxels=torch.empty((rows, self.max_pts, C), dtype=_F32, device=dev),
+                   coords=torch.empty((rows, 4), dtype=_I32, device=dev),
+                   num_points=torch.empty((rows,), dtype=_I32, device=dev),
+                   voxel_offsets=torch.zeros((self.B + 1,), dtype=_I32, device=dev))
+        out["mean"] = torch.empty((rows, C), dtype=_F32, device=dev) if with_mean else None
+        return out
+
+    def run(self, points, frame_offsets, max_frame_points, out, batch_size=None):
+        """points (total, C) f32 CUDA; frame_offsets (B+1) int32 CUDA. No host sync."""
+        pts = _cuda_f32(points, "points")
+        off = _cuda_i32(frame_offsets, "frame_offsets")
+        B = self.B if batch_size is None else int(batch_size)
+        if off.numel() != B + 1 or B > self.B:
+            raise V3DError("frame_offsets must have batch_size+1 entries (<= capacity)")
+        total, C = pts.shape
+        if self._calls >= (1 << 24) - 4:
+            self._init_ws()
+        self._calls += 1
+        mean = out.get("mean")
+        with torch.cuda.device(self.device):
+            check(_lib.load().v3d_voxelize_batch(
+                pts.data_ptr(), total, int(max_frame_points), C, off.data_ptr(), B,
+                f3(self.range[:3]), f3(self.voxel_size), i3(self.grid), self.max_pts, self.max_voxels,
+                self.cap_policy, out["voxels"].data_ptr(), out["coords"].data_ptr(),
+                out["num_points"].data_ptr(), out["voxel_offsets"].data_ptr(),
+                mean.data_ptr() if mean is not None else None, self.ws.data_ptr(), self.ws.numel(), self.P,
+                _stream()), "v3d_voxelize_batch")
+        return out
+
+
+# =============================================================================================
+# a3-a6: site table, rule book, sparse conv, dense
+# =============================================================================================
+class SiteTable:
+    """Device hash of the active sites of one resolution level (shared by the SubM layers with the
+    same indice_key and the strided conv leaving the level)."""
+
+    def __init__(self, capacity_rows, device):
+        self.capacity = int(capacity_rows)
+        self.device = torch.device(device)
+        nbytes = _lib.load().v3d_site_table_bytes(self.capacity)
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            check(_lib.load().v3d_site_table_init(self.buf.data_ptr(), self.buf.numel(), self.capacity, _stream()),
+                  "v3d_site_table_init")
+
+    def build(self, indices, n_rows, shape):
+        with torch.cuda.device(self.device):
+            check(_lib.load().v3d_site_table_build(self.buf.data_ptr(), indices.data_ptr(), n_rows.data_ptr(),
+                                                   self.capacity, i3(shape), _stream()), "v3d_site_table_build")
+        return self
+
+
+def conv_out_shape(shape, ksize, stride, padding, dilation):
+    out = (ctypes.c_int * 3)()
+    _lib.load().v3d_conv_out_shape(i3(shape), i3(ksize), i3(stride), i3(padding), i3(dilation), out)
+    return [int(x) for x in out]
+
+
+def rulebook_subm(table, indices, n_rows, shape, ksize, dilation, nbr=None):
+    """nbr (KV, capacity) int32: nbr[kk, o] = input row or -1. Outputs == inputs."""
+    ks, dl = _triple(ksize), _triple(dilation)
+    kv = ks[0] * ks[1] * ks[2]
+    cap = table.capacity
+    if nbr is None:
+        nbr = torch.empty((kv, cap), dtype=_I32, device=indices.device)
+    with torch.cuda.device(indices.device):
+        check(_lib.load().v3d_rulebook_subm(table.buf.data_ptr(), indices.data_ptr(), n_rows.data_ptr(), cap,
+                                            i3(shape), i3(ks), i3(dl), nbr.data_ptr(), nbr.shape[1], _stream()),
+              "v3d_rulebook_subm")
+    return nbr
+
+
+class ConvRulebookWorkspace:
+    def __init__(self, batch_size, out_shape, out_capacity, kernel_volume, device):
+        nbytes = _lib.load().v3d_rulebook_conv_workspace_bytes(int(batch_size), i3(out_shape), int(out_capacity),
+                                                               int(kernel_volume))
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+
+def rulebook_conv(in_table, indices, n_rows, batch_size, shape, ksize, stride, padding, dilation, out_capacity,
+                  out_indices=None, n_out=None, nbr=None, workspace=None):
+    ks, st, pd, dl = _triple(ksize), _triple(stride), _triple(padding), _triple(dilation)
+    kv = ks[0] * ks[1] * ks[2]
+    dev = indices.device
+    out_shape = conv_out_shape(shape, ks, st, pd, dl)
+    if out_indices is None:
+        out_indices = torch.empty((out_capacity, 4), dtype=_I32, device=dev)
+    if n_out is None:
+        n_out = torch.zeros(1, dtype=_I32, device=dev)
+    if nbr is None:
+        nbr = torch.empty((kv, out_capacity), dtype=_I32, device=dev)
+    if workspace is None:
+        workspace = ConvRulebookWorkspace(batch_size, out_shape, out_capacity, kv, dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().v3d_rulebook_conv(
+            in_table.buf.data_ptr(), indices.data_ptr(), n_rows.data_ptr(), in_table.capacity, int(batch_size),
+            i3(shape), i3(ks), i3(st), i3(pd), i3(dl), out_indices.data_ptr(), n_out.data_ptr(),
+            int(out_capacity), nbr.data_ptr(), nbr.shape[1], workspace.buf.data_ptr(), workspace.buf.numel(),
+            _stream()), "v3d_rulebook_conv")
+    return out_indices, n_out, nbr, out_shape
+
+
+def sparse_conv(feat, weight, nbr, n_out, out_capacity, scale=None, shift=None, relu=False, out=None):
+    """feat (rows, Cin); weight (KV, Cin, Cout) or spconv's (k0,k1,k2,Cin,Cout); nbr (KV, stride)."""
+    cin, cout = weight.shape[-2], weight.shape[-1]
+    kv = weight.numel() // (cin * cout)
+    if out is None:
+        out = torch.empty((out_capacity, cout), dtype=_F32, device=feat.device)
+    with torch.cuda.device(feat.device):
+        check(_lib.load().v3d_sparse_conv_fwd(
+            feat.data_ptr(), weight.data_ptr(), nbr.data_ptr(), nbr.shape[1], n_out.data_ptr(), int(out_capacity),
+            kv, cin, cout, scale.data_ptr() if scale is not None else None,
+            shift.data_ptr() if shift is not None else None, int(bool(relu)), out.data_ptr(), _stream()),
+            "v3d_sparse_conv_fwd")
+    return out
+
+
+def sparse_to_dense(feat, indices, n_rows, capacity_rows, batch_size, shape, out=None, workspace=None):
+    C = feat.shape[1]
+    dev = feat.device
+    if out is None:
+        out = torch.empty((batch_size, C, shape[0], shape[1], shape[2]), dtype=_F32, device=dev)
+    if workspace is None:
+        nbytes = _lib.load().v3d_sparse_to_dense_workspace_bytes(int(batch_size), i3(shape))
+        workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().v3d_sparse_to_dense(feat.data_ptr(), indices.data_ptr(), n_rows.data_ptr(),
+                                              int(capacity_rows), C, int(batch_size), i3(shape), out.data_ptr(),
+                                              workspace.data_ptr(), workspace.numel(), _stream()),
+              "v3d_sparse_to_dense")
+    return out
+
+
+# =============================================================================================
+# a7-a10: point ops (pointnet2_utils names and argument order)
+# =============================================================================================
+def furthest_point_sample(xyz, npoint):
+    x = _cuda_f32(xyz, "xyz", 3)
+    B, N, _ = x.shape
+    out = torch.empty((B, int(npoint)), dtype=_I32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.load().v3d_fps(x.data_ptr(), B, N, int(npoint), out.data_ptr(), None, 0, _stream()), "v3d_fps")
+    return out
+
+
+def gather_operation(features, idx):
+    f = _cuda_f32(features, "features")
+    i = _cuda_i32(idx, "idx")
+    B, C, N = f.shape
+    m = i.shape[1]
+    out = torch.empty((B, C, m), dtype=_F32, device=f.device)
+    with torch.cuda.device(f.device):
+        check(_lib.load().v3d_gather(f.data_ptr(), i.data_ptr(), B, C, N, m, out.data_ptr(), _stream()),
+              "v3d_gather")
+    return out
+
+
+def ball_query(radius, nsample, xyz, new_xyz):
+    x = _cuda_f32(xyz, "xyz", 3)
+    q = _cuda_f32(new_xyz, "new_xyz", 3)
+    B, N, _ = x.shape
+    M = q.shape[1]
+    out = torch.empty((B, M, int(nsample)), dtype=_I32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.load().v3d_ball_query(x.data_ptr(), q.data_ptr(), B, N, M, float(radius), int(nsample),
+                                         out.data_ptr(), _stream()), "v3d_ball_query")
+    return out
+
+
+def grouping_operation(features, idx):
+    f = _cuda_f32(features, "features")
+    i = _cuda_i32(idx, "idx")
+    B, C, N = f.shape
+    _, M, ns = i.shape
+    out = torch.empty((B, C, M, ns), dtype=_F32, device=f.device)
+    with torch.cuda.device(f.device):
+        check(_lib.load().v3d_group(f.data_ptr(), i.data_ptr(), B, C, N, M, ns, out.data_ptr(), _stream()),
+              "v3d_group")
+    return out
+
+
+def query_and_group(xyz, new_xyz, features, idx):
+    """[xyz[idx] - new_xyz ; features[idx]] -> (B, 3+C, M, ns)  (QueryAndGroup, use_xyz=True)."""
+    x = _cuda_f32(xyz, "xyz", 3)
+    q = _cuda_f32(new_xyz, "new_xyz", 3)
+    i = _cuda_i32(idx, "idx")
+    B, N, _ = x.shape
+    _, M, ns = i.shape
+    if features is not None:
+        f = _cuda_f32(features, "features")
+        C = f.shape[1]
+    else:
+        f, C = None, 0
+    out = torch.empty((B, 3 + C, M, ns), dtype=_F32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.load().v3d_query_and_group(x.data_ptr(), q.data_ptr(), f.data_ptr() if f is not None else None,
+                                              i.data_ptr(), B, C, N, M, ns, out.data_ptr(), _stream()),
+              "v3d_query_and_group")
+    return out
