@@ -99,8 +99,8 @@ V3D_API int v3d_nms_rotated(const float* dets, const float* scores, int N, float
  *   voxel_offsets (B+1) int32 device: frame b owns voxel rows [vo[b], vo[b+1])
  *   mean       (rows, C) f32 = sum over slots / num_points, or NULL to skip (a2)
  * The workspace is persistent: initialise once with v3d_voxelize_workspace_init and pass the
- * same buffer to every call (it carries an epoch so no per-call clearing is needed); it must be
- * re-initialised after 2^24-2 calls.
+ * same buffer to every call (it carries a device-side 32-bit call counter / epoch, so no per-call
+ * clearing is needed and CUDA-graph replays stay correct); re-initialise after 2^32-1 calls.
  * ------------------------------------------------------------------------------------------- */
 V3D_API size_t v3d_voxelize_workspace_bytes(int total_points_capacity, int B);
 V3D_API int v3d_voxelize_workspace_init(void* workspace, size_t workspace_bytes,

@@ -46,7 +46,7 @@ def test_iou_random_vs_oracle_bit_exact(cuda, m, n):
     b1, b2 = mk(m), mk(n)
     got = ops.box_iou_rotated(_t(b1, cuda), _t(b2, cuda)).cpu().numpy()
     want = oracle.box_iou_rotated(b1, b2, 1)
-    assert (want > 0).sum() > 0
+    assert m * n < 1000 or (want > 0).sum() > 0
     assert np.array_equal(_bits(got), _bits(want))
 
 

@@ -1,0 +1,172 @@
+"""GPU tests of the end-to-end SECOND path: the production engine (static buffers, CUDA graph) against the
+CPU port of the reference stack (oracle/second_cpu.py), the reference-shaped eager path built on the
+compat `spconv` drop-in, and the drop-in modules themselves."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import second_cpu
+from vision3d_b200 import second, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def no_tf32():
+    a, b = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = a, b
+
+
+def _match(a, b, tol_xy=2e-2, tol_s=2e-3):
+    """fraction of detections in a (boxes, bidx, cidx, scores) that have a partner in b"""
+    if len(a[0]) == 0:
+        return 1.0
+    hit = 0
+    for i in range(len(a[0])):
+        m = (b[1] == a[1][i]) & (b[2] == a[2][i])
+        if not m.any():
+            continue
+        d = np.abs(b[0][m][:, :2] - a[0][i, :2]).max(1)
+        s = np.abs(b[3][m] - a[3][i])
+        hit += bool(((d < tol_xy) & (s < tol_s)).any())
+    return hit / len(a[0])
+
+
+@pytest.mark.parametrize("cfg_name,B", [("car", 2), ("three", 1)])
+def test_engine_vs_cpu_port(cuda, no_tf32, cfg_name, B):
+    cfg = second.car_config() if cfg_name == "car" else second.three_class_config()
+    model = second.init_for_benchmark(second.SecondB200(cfg), 1)
+    clouds = synth.make_batch(10, B, 16384)
+    stages = {}
+    cpu_model = second.init_for_benchmark(second.SecondB200(cfg), 1).eval()
+    want = second_cpu.infer(cpu_model, clouds, second.make_anchors(cfg), nms_variant="oracle", stages=stages)
+    for use_graph in (False, True):
+        eng = second.SecondEngine(model, B, B * 16384, cuda, use_graph=use_graph).capture()
+        got = eng.infer(clouds)
+        # level counts and the dense BEV map come only from vision3d_b200 kernels: tight tolerance
+        assert int(eng.n_rows[0].item()) == stages["n_voxels"]
+        bev = eng.dense_out.view(B, -1, 200, 176).cpu()
+        ref = stages["bev"]
+        assert torch.equal(bev != 0, ref != 0) or ((bev != 0) ^ (ref != 0)).float().mean() < 1e-4
+        assert (bev - ref).abs().max() <= 1e-4 * ref.abs().max()
+        # detections: RPN runs in cuDNN vs CPU MKL -> compare as matched sets
+        assert abs(len(got[0]) - len(want[0])) <= max(2, len(want[0]) // 20)
+        assert _match(got, want) >= 0.9 and _match(want, got) >= 0.9
+        # replay determinism
+        r1 = eng.h_result.clone()
+        eng.infer(clouds)
+        assert torch.equal(r1, eng.h_result)
+
+
+def test_eager_compat_path_equals_engine(cuda, no_tf32):
+    """SecondB200.inference on the compat spconv drop-in, fed exactly like the reference's Preprocessor
+    feeds Second (voxels/coords/occupancy from VoxelGenerator.generate), vs the fused engine."""
+    from vision3d_b200.compat import spconv
+    cfg = second.car_config()
+    model = second.init_for_benchmark(second.SecondB200(cfg), 2).to(cuda).eval()
+    clouds = synth.make_batch(20, 2, 16384)
+    gen = spconv.utils.VoxelGenerator(cfg.VOXEL_SIZE, cfg.GRID_BOUNDS, cfg.MAX_OCCUPANCY, cfg.MAX_VOXELS)
+    f, c, o = [], [], []
+    for i, p in enumerate(clouds):
+        v, cc, n = gen.generate(p)
+        vo, co, no = oracle.voxelize(p, cfg.VOXEL_SIZE, cfg.GRID_BOUNDS, cfg.MAX_OCCUPANCY, cfg.MAX_VOXELS)
+        assert np.array_equal(v, vo) and np.array_equal(cc, co) and np.array_equal(n, no)
+        f.append(v)
+        c.append(np.pad(cc, ((0, 0), (1, 0)), constant_values=i))
+        o.append(n)
+    item = dict(features=torch.from_numpy(np.concatenate(f)).to(cuda),
+                coordinates=torch.from_numpy(np.concatenate(c)).to(cuda),
+                occupancy=torch.from_numpy(np.concatenate(o)).to(cuda), batch_size=2,
+                anchors=second.make_anchors(cfg).to(cuda))
+    with torch.no_grad():
+        boxes, bidx, cidx, scores = model.inference(item)
+    eng = second.SecondEngine(model, 2, 2 * 16384, cuda, use_graph=True).capture()
+    got = eng.infer(clouds)
+    assert len(got[0]) == len(boxes)
+    order = np.lexsort((-got[3], got[1]))
+    ref_order = np.lexsort((-scores.cpu().numpy(), bidx.cpu().numpy()))
+    np.testing.assert_allclose(got[0][order], boxes.cpu().numpy()[ref_order], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(got[3][order], scores.cpu().numpy()[ref_order], rtol=1e-4, atol=1e-5)
+
+
+def test_spconv_dropin_api(cuda):
+    """The surface vision3d uses: nestable/indexable SparseSequential, SubMConv3d with the stray
+    positional stride, tuple kernel/stride/padding, .dense(), eval-mode BN folding == unfolded."""
+    from vision3d_b200.compat import spconv
+    from torch import nn
+    shape, B = [9, 30, 28], 2
+    idx = synth.make_clustered_sites(1, 500, shape, B)
+    feats = torch.randn(len(idx), 4, device=cuda)
+    net = spconv.SparseSequential(
+        spconv.SparseSequential(spconv.SubMConv3d(4, 16, 3, 3, indice_key="subm0", bias=False),
+                                nn.BatchNorm1d(16, eps=1e-3, momentum=0.01), nn.ReLU()),
+        spconv.SparseSequential(spconv.SubMConv3d(16, 16, 3, 3, indice_key="subm0", bias=False),
+                                nn.BatchNorm1d(16, eps=1e-3, momentum=0.01), nn.ReLU()),
+        spconv.SparseSequential(spconv.SparseConv3d(16, 32, (3, 1, 1), (2, 1, 1), padding=[0, 0, 0], bias=False),
+                                nn.BatchNorm1d(32, eps=1e-3, momentum=0.01), nn.ReLU()),
+    ).to(cuda)
+    for m in net.modules():
+        if isinstance(m, nn.BatchNorm1d):
+            m.running_mean.normal_()
+            m.running_var.uniform_(0.5, 2)
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.normal_()
+    assert isinstance(net[0][0], spconv.SubMConv3d) and len(net) == 3
+    x = spconv.SparseConvTensor(feats, torch.from_numpy(idx).to(cuda), shape, B)
+    net.eval()
+    with torch.no_grad():
+        y = net(x)
+        d = y.dense()
+        assert d.shape == (B, 32, 4, 30, 28)
+        # unfolded reference: run modules one by one (no BN folding)
+        z = spconv.SparseConvTensor(feats, torch.from_numpy(idx).to(cuda), shape, B)
+        for blk in net:
+            z = blk[0](z)
+            z.features = blk[2](blk[1](z.features))
+        assert torch.allclose(y.features, z.features, rtol=1e-4, atol=1e-5)
+    # training mode: autograd through the sparse conv (torch-composed backward)
+    net.train()
+    feats.requires_grad_(True)
+    out = net(spconv.SparseConvTensor(feats, torch.from_numpy(idx).to(cuda), shape, B))
+    out.features.sum().backward()
+    assert feats.grad is not None and net[0][0].weight.grad is not None
+
+
+def test_pointnet2_dropin(cuda):
+    from vision3d_b200.compat.pointnet2 import pointnet2_modules, pointnet2_utils
+    from copy import deepcopy
+    xyz = torch.from_numpy(np.stack([c[:4096, :3] for c in synth.make_batch(0, 2)], 0)).to(cuda)
+    idx = pointnet2_utils.furthest_point_sample(xyz, 128)
+    assert idx.dtype == torch.int32 and idx.shape == (2, 128)
+    kp = pointnet2_utils.gather_operation(xyz.transpose(1, 2).contiguous(), idx).transpose(1, 2).contiguous()
+    assert torch.equal(kp[0, 5], xyz[0, idx[0, 5].long()])
+    mlps = [[4, 8, 16], [4, 8, 16]]
+    sa = pointnet2_modules.PointnetSAModuleMSG(npoint=-1, radii=[0.4, 0.8], nsamples=[16, 32], mlps=deepcopy(mlps),
+                                               use_xyz=True).to(cuda).eval()
+    feats = torch.randn(2, 4, 4096, device=cuda)
+    with torch.no_grad():
+        new_xyz, out = sa(xyz, feats, kp)
+    assert out.shape == (2, 32, 128) and new_xyz is kp
+    # grouped tensor equals the oracle's
+    g = sa.groupers[0](xyz, kp, feats).cpu().numpy()
+    want_idx = oracle.ball_query(0.4, 16, xyz.cpu().numpy(), kp.cpu().numpy())
+    want = oracle.query_and_group(xyz.cpu().numpy(), kp.cpu().numpy(), feats.cpu().numpy(), want_idx)
+    assert np.array_equal(g, want)
+
+
+def test_c_ext_and_searchsorted_shims(cuda):
+    from vision3d_b200.compat import c_ext, torchsearchsorted
+    b = torch.tensor([[0, 0, 2, 2, 0], [1, 1, 2, 2, 0], [0, 0, 2, 2, 45], [10, 10, 2, 2, 0]], dtype=torch.float32,
+                     device=cuda)
+    iou = c_ext.box_iou_rotated(b[:1], b)
+    assert abs(float(iou[0, 1]) - 1 / 7) < 1e-6 and abs(float(iou[0, 2]) - 0.70710678) < 1e-6
+    keep = c_ext.nms_rotated(b, torch.tensor([.9, .8, .7, .6], device=cuda), 0.1)
+    assert keep.tolist() == [0, 3] and keep.dtype == torch.int64 and keep.is_cuda
+    assert c_ext.get_cuda_version().startswith("12.")
+    a = torch.tensor([[0, 0, 1, 1, 1, 3]], dtype=torch.int32, device=cuda)
+    v = torch.arange(5, dtype=torch.int32, device=cuda)[None]
+    assert torchsearchsorted.searchsorted(a, v).tolist() == [[0, 2, 5, 5, 6]]

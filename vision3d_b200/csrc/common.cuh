@@ -42,9 +42,18 @@ __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a -
 // Epoch-tagged open-addressing hash keyed by a <=40-bit integer.
 // Entry = [epoch:24 | key:40]. Entries written under an older epoch read as empty, so a table
 // is "cleared" by bumping the epoch: no per-call memset traffic. Linear probing.
+// The tables keep a 32-bit call counter; the 24-bit key epoch is derived from it (epoch24()), and every
+// payload word carries the full 32-bit counter as its tag. When the 24-bit epoch recurs (every 2^24-1
+// calls) a never-overwritten entry from that era can look live in `keys`; that is harmless by
+// construction: it either holds the same key (claiming is idempotent, payload tags still mismatch)
+// or acts as a tombstone (tables are sized >= 4x the rows, so load stays <= 50 %).
 // ---------------------------------------------------------------------------------------------
 constexpr int kKeyBits = 40;
 constexpr unsigned long long kKeyMask = (1ull << kKeyBits) - 1ull;
+
+__host__ __device__ __forceinline__ unsigned int epoch24(unsigned int calls) {
+  return calls % 0xFFFFFFu + 1u;
+}
 
 __device__ __forceinline__ unsigned int hash_key(unsigned long long k) {
   k ^= k >> 33;

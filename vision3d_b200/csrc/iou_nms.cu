@@ -268,9 +268,11 @@ __global__ void __launch_bounds__(256) nms_rank_kernel(const float* __restrict__
   }
 }
 
-// (2) upper-triangular mask tiles. Block = 256 threads = 8 warps; warp w owns rows w*8..w*8+7 of
+// (2) upper-triangular mask tiles. Block = 512 threads = 16 warps; warp w owns rows w*4..w*4+3 of
 //     the 64-row tile, lanes cover columns lane and lane+32; __ballot_sync assembles the words.
-__global__ void __launch_bounds__(256) nms_mask_kernel(const BoxPre* __restrict__ pre, int N, float thr,
+constexpr int kMaskThreads = 512;
+constexpr int kMaskRowsPerWarp = kTile / (kMaskThreads / 32);
+__global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(const BoxPre* __restrict__ pre, int N, float thr,
                                                        int col_blocks,
                                                        unsigned long long* __restrict__ mask) {
   const int rb = blockIdx.y, cb = blockIdx.x;
@@ -288,8 +290,8 @@ __global__ void __launch_bounds__(256) nms_mask_kernel(const BoxPre* __restrict_
   const int lane = tid & 31, warp = tid >> 5;
   const int ncol = min(kTile, N - cb * kTile);
 #pragma unroll 1
-  for (int rr = 0; rr < 8; rr++) {
-    const int r = warp * 8 + rr;
+  for (int rr = 0; rr < kMaskRowsPerWarp; rr++) {
+    const int r = warp * kMaskRowsPerWarp + rr;
     const int gi = rb * kTile + r;
     if (gi >= N) break;  // warp-uniform
     const BoxPre a = rbox[r];
@@ -348,16 +350,19 @@ __global__ void __launch_bounds__(1024) nms_scan_kernel(const unsigned long long
       int pos = base + __popcll(kept & ((1ull << tid) - 1ull));
       keep[pos] = (long long)order[b * kTile + tid];
     }
-    // suppress: OR rows of kept boxes into later words
-    for (int j = b + 1 + tid; j < col_blocks; j += blockDim.x) {
-      unsigned long long acc = remv[j];
-      unsigned long long k = kept;
-      while (k) {
-        int i = __ffsll((long long)k) - 1;
-        k &= k - 1;
-        acc |= mask[(size_t)(b * kTile + i) * col_blocks + j];
+    // suppress: OR the rows of kept boxes into the later words. One warp per kept row, lanes along
+    // the row's contiguous words: every load of the chunk is in flight at once (one global round
+    // trip per chunk instead of one per kept row), merged with shared-memory atomics.
+    {
+      const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+      for (int i = warp; i < rows; i += nwarps) {
+        if (!((kept >> i) & 1ull)) continue;
+        const unsigned long long* row = mask + (size_t)(b * kTile + i) * col_blocks;
+        for (int j = b + 1 + lane; j < col_blocks; j += 32) {
+          const unsigned long long m = row[j];
+          if (m) atomicOr(&remv[j], m);
+        }
       }
-      remv[j] = acc;
     }
     __syncthreads();
     if (tid == 0) kept_base = base + __popcll(kept);
@@ -420,8 +425,8 @@ extern "C" int v3d_nms_rotated(const float* dets, const float* scores, int N, fl
   const int cb = ceil_div(N, kTile);
 
   nms_rank_kernel<<<ceil_div(N, 256), 256, 0, st>>>(dets, scores, N, order, pre);
-  nms_mask_kernel<<<dim3(cb, cb), 256, 0, st>>>(pre, N, iou_threshold, cb, mask);
-  int scan_threads = cb <= 128 ? 128 : (cb <= 256 ? 256 : (cb <= 512 ? 512 : 1024));
+  nms_mask_kernel<<<dim3(cb, cb), kMaskThreads, 0, st>>>(pre, N, iou_threshold, cb, mask);
+  const int scan_threads = 1024;  // 32 warps: two kept rows per warp in the suppress phase
   nms_scan_kernel<<<1, scan_threads, sizeof(unsigned long long) * cb, st>>>(
       mask, order, N, cb, reinterpret_cast<long long*>(keep), num_keep);
   return check_launch();

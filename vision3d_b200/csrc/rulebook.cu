@@ -25,7 +25,7 @@ struct TableHeader {
 struct SiteTable {
   TableHeader* hdr;
   unsigned long long* keys;
-  int* vals;
+  unsigned long long* vals;  // [calls:32 | row:32]
   unsigned int cap;
   size_t total;
 };
@@ -33,14 +33,14 @@ struct SiteTable {
 inline SiteTable table_layout(void* base, int capacity_rows) {
   SiteTable t;
   char* p = static_cast<char*>(base);
-  t.cap = next_pow2((unsigned int)(2 * (size_t)(capacity_rows > 512 ? capacity_rows : 512)));
+  t.cap = next_pow2((unsigned int)(4 * (size_t)(capacity_rows > 512 ? capacity_rows : 512)));
   size_t off = 0;
   t.hdr = reinterpret_cast<TableHeader*>(p + off);
   off = align_up(off + sizeof(TableHeader), 256);
   t.keys = reinterpret_cast<unsigned long long*>(p + off);
   off = align_up(off + 8ull * t.cap, 256);
-  t.vals = reinterpret_cast<int*>(p + off);
-  off = align_up(off + 4ull * t.cap, 256);
+  t.vals = reinterpret_cast<unsigned long long*>(p + off);
+  off = align_up(off + 8ull * t.cap, 256);
   t.total = off;
   return t;
 }
@@ -59,11 +59,12 @@ __global__ void __launch_bounds__(256) table_build_kernel(SiteTable T, const int
                                                           const int* __restrict__ n_rows, int cap_rows,
                                                           Shape3 shape) {
   const int n = min(*n_rows, cap_rows);
-  const unsigned int epoch = T.hdr->epoch;
+  const unsigned int calls = T.hdr->epoch;
+  const unsigned int epoch = epoch24(calls);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     int4 c = idx[i];
     unsigned int s = table_claim(T.keys, T.cap - 1, epoch, flat_key(c.x, c.y, c.z, c.w, shape));
-    T.vals[s] = i;
+    T.vals[s] = ((unsigned long long)calls << 32) | (unsigned int)i;
   }
 }
 
@@ -82,7 +83,8 @@ __global__ void __launch_bounds__(256) rule_lookup_kernel(SiteTable T, const int
   const int n = min(*n_out, out_cap);
   const int kk = blockIdx.y;
   const int kx = kk % G.ks[2], ky = (kk / G.ks[2]) % G.ks[1], kz = kk / (G.ks[2] * G.ks[1]);
-  const unsigned int epoch = T.hdr->epoch;
+  const unsigned int calls = T.hdr->epoch;
+  const unsigned int epoch = epoch24(calls);
   Shape3 ish{{G.in_shape[0], G.in_shape[1], G.in_shape[2]}};
   for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n; o += gridDim.x * blockDim.x) {
     int r;
@@ -96,7 +98,10 @@ __global__ void __launch_bounds__(256) rule_lookup_kernel(SiteTable T, const int
       r = -1;
       if (z >= 0 && z < G.in_shape[0] && y >= 0 && y < G.in_shape[1] && x >= 0 && x < G.in_shape[2]) {
         unsigned int s = table_find(T.keys, T.cap - 1, epoch, flat_key(c.x, z, y, x, ish));
-        if (s != 0xFFFFFFFFu) r = __ldg(&T.vals[s]);
+        if (s != 0xFFFFFFFFu) {
+          const unsigned long long v = __ldg(&T.vals[s]);
+          if ((unsigned int)(v >> 32) == calls) r = (int)(unsigned int)v;  // else: stale alias, not a site
+        }
       }
     }
     nbr[(size_t)kk * nbr_stride + o] = r;

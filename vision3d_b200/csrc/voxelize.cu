@@ -52,7 +52,7 @@ inline VoxWs vox_layout(void* base, int P, int B) {
   VoxWs w;
   char* p = static_cast<char*>(base);
   size_t off = 0;
-  w.cap = next_pow2((unsigned int)(2 * (size_t)(P > 512 ? P : 512)));
+  w.cap = next_pow2((unsigned int)(4 * (size_t)(P > 512 ? P : 512)));
   w.cpf_cap = ceil_div(P > 1 ? P : 1, kChunk);
   auto take = [&](size_t bytes) {
     char* r = p + off;
@@ -99,7 +99,8 @@ __global__ void __launch_bounds__(kChunk) vox_insert_kernel(const float* __restr
   const int il = blockIdx.x * kChunk + threadIdx.x;
   if (il >= n) return;
   const size_t g = (size_t)start + il;
-  const unsigned int epoch = W.hdr->epoch;
+  const unsigned int calls = W.hdr->epoch;  // 32-bit call counter; key epoch derived from it
+  const unsigned int epoch = epoch24(calls);
   int c[3];
   float pt[3];
   pt[0] = points[g * P.C + 0];
@@ -112,10 +113,10 @@ __global__ void __launch_bounds__(kChunk) vox_insert_kernel(const float* __restr
   unsigned long long cell = ((unsigned long long)c[2] * P.grid[1] + c[1]) * P.grid[0] + c[0];
   unsigned long long key = (unsigned long long)b * P.cells + cell;
   unsigned int s = table_claim(W.keys, W.cap - 1, epoch, key);
-  const unsigned long long tag = (unsigned long long)epoch << 32;
+  const unsigned long long tag = (unsigned long long)calls << 32;
   atomicMax(&W.firstmax[s], tag | (unsigned long long)(~(unsigned int)il));
   unsigned long long old = atomicExch(&W.head[s], tag | (unsigned long long)(unsigned int)il);
-  W.pt_next[g] = ((unsigned int)(old >> 32) == epoch) ? (int)(unsigned int)old : -1;
+  W.pt_next[g] = ((unsigned int)(old >> 32) == calls) ? (int)(unsigned int)old : -1;
   W.pt_slot[g] = s;
 }
 

@@ -151,9 +151,6 @@ class Voxelizer:
         if off.numel() != B + 1 or B > self.B:
             raise V3DError("frame_offsets must have batch_size+1 entries (<= capacity)")
         total, C = pts.shape
-        if self._calls >= (1 << 24) - 4:
-            self._init_ws()
-        self._calls += 1
         mean = out.get("mean")
         with torch.cuda.device(self.device):
             check(_lib.load().v3d_voxelize_batch(
