@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=16, help="frames per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--simt", action="store_true", help="exact-fp32 SIMT sparse conv instead of tcgen05 3xTF32")
     return ap.parse_args()
 
 
@@ -212,7 +213,8 @@ def run_b200(args):
     B = args.batch
     cfg = second.car_config()
     model = second.init_for_benchmark(second.SecondB200(cfg), 0)
-    eng = second.SecondEngine(model, B, B * PTS_PER_FRAME, dev, use_graph=not args.no_graph).capture()
+    eng = second.SecondEngine(model, B, B * PTS_PER_FRAME, dev, use_graph=not args.no_graph,
+                              tensor_cores=not args.simt).capture()
 
     # distinct synthetic batches per rank, staged in pinned host memory and mirrored on the device
     n_sets = 4
@@ -333,7 +335,9 @@ def run_b200(args):
                        "l2": "no explicit flush: per-step working set (dense BEV %.0f MB + RPN activations) is "
                              "far larger than the 126 MB L2; 4 distinct input batches rotate"
                              % (eng.dense_out.numel() * 4 / 1e6),
-                       "cuda_graph": eng.graph is not None, "rpn": "torch/cuDNN fp32 (TF32 allowed=%s)"
+                       "cuda_graph": eng.graph is not None,
+                       "sparse_conv": "exact-fp32 SIMT" if args.simt else "tcgen05 kind::tf32 3xTF32 (Cin>=16), "
+                                                                          "exact-fp32 SIMT (Cin=4)", "rpn": "torch/cuDNN fp32 (TF32 allowed=%s)"
                                                                    % torch.backends.cudnn.allow_tf32,
                        "active_sites_per_level": rows, "detections": int(counts["kept"])},
             "e2e": {"value": round(e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": eng.h2d_bytes(),

@@ -160,6 +160,19 @@ V3D_API int v3d_sparse_conv_fwd(const float* feat, const float* weight, const in
                                 int Cout, const float* scale, const float* shift, int relu, float* out,
                                 v3d_stream_t stream);
 
+/* Tensor-core path of the same op (tcgen05.mma kind::tf32 with a 3xTF32 split, accumulators in TMEM;
+ * relative error of a product ~2^-21, results within 1e-5 of the exact-fp32 path). Weights are prepared
+ * once per layer into the shared-memory image the kernel streams with 1-D TMA:
+ *   v3d_sparse_conv_prepared_bytes returns 0 for shapes only the exact-fp32 path supports (Cin < 16 ...).
+ * Supported: kernel_volume <= 32, Cin and Cout in {16, 32, 64}. */
+V3D_API size_t v3d_sparse_conv_prepared_bytes(int kernel_volume, int Cin, int Cout);
+V3D_API int v3d_sparse_conv_prepare(const float* weight, int kernel_volume, int Cin, int Cout, void* prepared,
+                                    size_t prepared_bytes, v3d_stream_t stream);
+V3D_API int v3d_sparse_conv_fwd_tc(const float* feat, const void* prepared, const int* nbr, int nbr_stride,
+                                   const int* n_out, int out_capacity, int kernel_volume, int Cin, int Cout,
+                                   const float* scale, const float* shift, int relu, float* out,
+                                   v3d_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * a3  SparseConvTensor.dense(): (N,C) rows -> (B,C,D,H,W), zero filled (sparse_cnn.py:128-133).
  * workspace holds the (B,D,H,W) int32 cell->row map.

@@ -384,3 +384,63 @@ def test_ball_query_group_gather_exact(cuda):
     fi = oracle.fps(xyz, 64)
     got = ops.gather_operation(_t(feat, cuda), _t(fi, cuda)).cpu().numpy()
     assert np.array_equal(_bits(got), _bits(oracle.gather(feat, fi)))
+
+
+# ------------------------------------------------------------------------------------ tcgen05 sparse conv
+def _conv_tc_case(cuda, cin, cout, subm, n_sites=3000, shape=(9, 60, 56), B=2, seed=0, bn=True):
+    """tcgen05 3xTF32 kernel vs the fp64-accumulating oracle (<= 1e-4 rel of max, expected ~1e-6) and vs
+    the exact-fp32 SIMT kernel."""
+    from vision3d_b200 import ops
+    rng = np.random.default_rng(seed)
+    shape = list(shape)
+    idx = synth.make_clustered_sites(seed + 11, n_sites, shape, B)
+    ind, n_rows, table, cap = _site_setup(cuda, idx, shape)
+    feat = rng.normal(size=(len(idx), cin)).astype(np.float32)
+    w = (rng.normal(size=(27, cin, cout)) / np.sqrt(9 * cin)).astype(np.float32)
+    fd = torch.zeros((cap, cin), device=cuda)
+    fd[:len(idx)] = _t(feat, cuda)
+    if subm:
+        nbr = ops.rulebook_subm(table, ind, n_rows, shape, 3, 1)
+        n_out, out_cap, want_nbr = n_rows, cap, oracle.rulebook_subm(idx, shape, 3)
+    else:
+        oi, want_nbr, _ = oracle.rulebook_conv(idx, shape, 3, 2, 1)
+        out_cap = len(oi) + 5
+        _, n_out, nbr, _ = ops.rulebook_conv(table, ind, n_rows, B, shape, 3, 2, 1, 1, out_cap)
+    scale = shift = None
+    if bn:
+        scale, shift = rng.uniform(0.5, 1.5, cout).astype(np.float32), rng.normal(size=cout).astype(np.float32)
+    sc, sh = (_t(scale, cuda), _t(shift, cuda)) if bn else (None, None)
+    pw = ops.PreparedWeights(_t(w, cuda))
+    assert pw.buf is not None
+    got = ops.sparse_conv(fd, pw, nbr, n_out, out_cap, sc, sh, relu=bn)
+    simt = ops.sparse_conv(fd, _t(w, cuda), nbr, n_out, out_cap, sc, sh, relu=bn)
+    want = oracle.sparse_conv(feat, w, want_nbr, scale, shift, bn)
+    n = len(want)
+    err = np.abs(got[:n].cpu().numpy() - want).max() / np.abs(want).max()
+    err_simt = (got[:n] - simt[:n]).abs().max().item() / np.abs(want).max()
+    assert err <= 1e-4, err
+    assert err_simt <= 2e-5, err_simt
+    return err
+
+
+@pytest.mark.parametrize("cin,cout", [(16, 16), (16, 32), (32, 32), (32, 64), (64, 64), (16, 64)])
+def test_sparse_conv_tc_subm(cuda, cin, cout):
+    err = _conv_tc_case(cuda, cin, cout, subm=True)
+    assert err < 1e-5, err  # 3xTF32 keeps fp32-grade accuracy
+
+
+@pytest.mark.parametrize("cin,cout", [(16, 32), (32, 64), (64, 64)])
+def test_sparse_conv_tc_strided(cuda, cin, cout):
+    _conv_tc_case(cuda, cin, cout, subm=False, bn=False)
+
+
+def test_sparse_conv_tc_many_tiles_and_tail(cuda):
+    """More tiles than SMs (persistent loop, TMEM double buffering) and a ragged last tile."""
+    _conv_tc_case(cuda, 64, 64, subm=True, n_sites=148 * 128 + 77, shape=(11, 120, 110), B=2, seed=5)
+    _conv_tc_case(cuda, 32, 32, subm=True, n_sites=130, shape=(5, 20, 20), B=1, seed=6)
+
+
+def test_prepared_weights_fall_back_to_exact_path_for_cin4(cuda):
+    from vision3d_b200 import ops
+    pw = ops.PreparedWeights(torch.randn(27, 4, 16, device=cuda))
+    assert pw.buf is None  # Cin = 4 stays on the exact-fp32 SIMT kernel

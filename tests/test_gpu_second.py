@@ -53,9 +53,18 @@ def test_engine_vs_cpu_port(cuda, no_tf32, cfg_name, B):
         ref = stages["bev"]
         assert torch.equal(bev != 0, ref != 0) or ((bev != 0) ^ (ref != 0)).float().mean() < 1e-4
         assert (bev - ref).abs().max() <= 1e-4 * ref.abs().max()
-        # detections: RPN runs in cuDNN vs CPU MKL -> compare as matched sets
-        assert abs(len(got[0]) - len(want[0])) <= max(2, len(want[0]) // 20)
-        assert _match(got, want) >= 0.9 and _match(want, got) >= 0.9
+        # NMS inside the pipeline: the engine's own candidates through the oracle must give its keep list
+        k = int(eng.count.item())
+        want_keep = oracle.nms_rotated(eng._nms_in.cpu().numpy(), eng._scores.cpu().numpy(), cfg.NMS_THRESH, 1)
+        assert np.array_equal(eng.keep[:k].cpu().numpy(), want_keep)
+        # candidates: RPN runs in cuDNN vs CPU MKL, so compare the per-(frame, class) score profiles
+        gs = eng._scores.view(B, cfg.NUM_CLASSES, -1).sort(-1, descending=True)[0].cpu()
+        cs = stages["cand_scores"].view(B, cfg.NUM_CLASSES, -1).sort(-1, descending=True)[0]
+        assert (gs - cs).abs().max() < 5e-3, (gs - cs).abs().max()
+        # final detections as matched sets (top-k / NMS decisions may flip on near ties across back ends)
+        fa, fb = _match(got, want), _match(want, got)
+        assert abs(len(got[0]) - len(want[0])) <= max(3, len(want[0]) // 10), (len(got[0]), len(want[0]))
+        assert fa >= 0.8 and fb >= 0.8, (fa, fb, len(got[0]), len(want[0]))
         # replay determinism
         r1 = eng.h_result.clone()
         eng.infer(clouds)

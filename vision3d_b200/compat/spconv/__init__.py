@@ -137,11 +137,13 @@ class _SparseConvFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, features, weight, nbr, n_out_dev, n_out, scale, shift, relu):
-        out = ops.sparse_conv(features.contiguous(), weight.contiguous(), nbr, n_out_dev, max(n_out, 1), scale,
-                              shift, relu)
-        ctx.save_for_backward(features, weight, nbr)
+        prepared = isinstance(weight, ops.PreparedWeights)
+        out = ops.sparse_conv(features.contiguous(), weight if prepared else weight.contiguous(), nbr, n_out_dev,
+                              max(n_out, 1), scale, shift, relu)
+        if not prepared:
+            ctx.save_for_backward(features, weight, nbr)
         ctx.n_out = n_out
-        ctx.fused = scale is not None or relu
+        ctx.fused = scale is not None or relu or prepared
         return out[:n_out]
 
     @staticmethod
@@ -250,7 +252,14 @@ class SparseConvolution(SparseModule):
         elif self.bias is not None:
             scale = torch.ones_like(self.bias)
             shift = self.bias
-        feats = _SparseConvFunction.apply(input.features, self.weight, nbr, n_out_dev, n_out,
+        weight = self.weight
+        if not (torch.is_grad_enabled() and (self.weight.requires_grad or input.features.requires_grad)):
+            # inference: tcgen05 path with the weight image prepared once per weight version
+            ver = (self.weight._version, self.weight.data_ptr())
+            if getattr(self, "_prepared_ver", None) != ver:
+                self._prepared, self._prepared_ver = ops.PreparedWeights(self.weight), ver
+            weight = self._prepared
+        feats = _SparseConvFunction.apply(input.features, weight, nbr, n_out_dev, n_out,
                                           scale.detach() if scale is not None else None,
                                           shift.detach() if shift is not None else None,
                                           bool(fold_relu and fold_bn is not None))

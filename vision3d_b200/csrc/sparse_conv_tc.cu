@@ -1,0 +1,471 @@
+// a5 + a6 on the 5th-generation tensor cores: output-stationary sparse convolution with tcgen05.mma
+// (kind::tf32, 3xTF32 split for fp32-grade accuracy), accumulators in TMEM, folded BN + ReLU epilogue.
+//
+// One persistent CTA per SM, warp specialised:
+//   warps 0-3  epilogue   : tcgen05.ld the 128 x COUT fp32 accumulator (lane = output row), apply
+//                           scale/shift/ReLU, store each output row once
+//   warp  4    MMA issuer : one elected thread; per pipeline slot issues 3*(CIN/8) tcgen05.mma
+//                           (A_hi*B_hi + A_lo*B_hi + A_hi*B_lo) M=128, N=COUT, K=8; tcgen05.commit
+//                           frees the slot / publishes the accumulator through mbarriers
+//   warp  5    weight TMA : one thread; cp.async.bulk (1-D TMA) of the pre-swizzled, pre-split W[kk]
+//                           image (hi+lo) into the slot, completion on the slot's mbarrier
+//   warps 6-9  gatherers  : stage the tile's rule rows (all KV offsets x 128 outputs), skip offsets
+//                           no row of the tile uses, gather the neighbour feature rows with 128-bit
+//                           loads, split every value into tf32 hi / lo parts and write them into
+//                           the 128B-swizzled K-major UMMA layout
+// Output rows are written exactly once (no atomics, deterministic). Arithmetic: every product is
+// exact in fp32 (11-bit x 11-bit mantissas); dropping only a_lo*b_lo bounds the relative error of a
+// product by ~2^-21, far inside the 1e-4 the contract allows.
+//
+// Shared-memory operand layout (both operands K-major, SWIZZLE_128B, fp32 elements): a "chunk" is
+// rows x 128 bytes (32 K-elements); 8-row groups are 1024 B apart (SBO); the 16-byte unit u of row r
+// lives at unit u ^ (r & 7). CIN = 64 uses two chunks, CIN = 16 uses half of one.
+#include "common.cuh"
+
+namespace v3d {
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kEpiWarps = 4, kGatherWarps = 4;
+constexpr int kThreads = 32 * (kEpiWarps + 2 + kGatherWarps);  // 320
+constexpr int kMaxKV = 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled K-major) | SBO>>4 [32,46) | version=1 [46,48)
+// | base_offset=0 [49,52) | layout_type=2 (SWIZZLE_128B) [61,64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  const uint32_t lo = ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16);
+  const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+  return (uint64_t)lo | ((uint64_t)hi << 32);
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=TF32 [7,10)=2, b=TF32 [10,13)=2,
+// a,b K-major (bits 15,16 = 0), N>>3 [17,23), M>>4 [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int CIN, int COUT>
+struct TcCfg {
+  static constexpr int kChunks = (CIN + 31) / 32;
+  static constexpr int kKSteps = CIN / 8;
+  static constexpr int kUnitsPerRow = CIN / 4;                      // 16-byte units in a feature row
+  static constexpr int kAChunkBytes = kTileM * 128;                 // 16 KB
+  static constexpr int kBChunkBytes = COUT * 128;
+  static constexpr int kAPartBytes = kChunks * kAChunkBytes;        // hi or lo
+  static constexpr int kBPartBytes = kChunks * kBChunkBytes;
+  static constexpr int kABytes = 2 * kAPartBytes;
+  static constexpr int kBBytes = 2 * kBPartBytes;                   // == one prepared W[kk] image
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (CIN >= 64) ? 2 : 3;
+  static constexpr int kTmemCols = (2 * COUT <= 32) ? 32 : (2 * COUT <= 64 ? 64 : (2 * COUT <= 128 ? 128 : 256));
+  static constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * kStageBytes +
+                                       sizeof(int) * kMaxKV * kTileM + 1024 /*barriers + meta*/;
+};
+
+struct SlotMeta {
+  int kk;    // kernel offset of this slot, or -1 = all tiles done
+  int last;  // 1 = last slot of its output tile
+};
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(kThreads, 1)
+sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __restrict__ wprep,
+                      const int* __restrict__ nbr, int nbr_stride, const int* __restrict__ n_out_ptr, int out_cap,
+                      int KV, const float* __restrict__ scale, const float* __restrict__ shift, int relu,
+                      float* __restrict__ out) {
+  using C = TcCfg<CIN, COUT>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* stages = base;                                             // kStages x (A_hi A_lo B_hi B_lo)
+  int* idx_tile = reinterpret_cast<int*>(base + (size_t)C::kStages * C::kStageBytes);  // [KV][128]
+  unsigned char* tail = reinterpret_cast<unsigned char*>(idx_tile + kMaxKV * kTileM);
+  uint64_t* full_a = reinterpret_cast<uint64_t*>(tail);          // [kStages]
+  uint64_t* full_b = full_a + 4;
+  uint64_t* empty = full_b + 4;
+  uint64_t* meta_full = empty + 4;
+  uint64_t* acc_full = meta_full + 4;   // [2]
+  uint64_t* acc_empty = acc_full + 2;   // [2]
+  SlotMeta* meta = reinterpret_cast<SlotMeta*>(acc_empty + 2);  // [kStages]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(meta + 4);
+  uint32_t* tile_mask = tmem_slot + 1;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_out = min(*n_out_ptr, out_cap);
+  const int n_tiles = (n_out + kTileM - 1) / kTileM;
+
+  if (tid == 0) {
+    for (int s = 0; s < C::kStages; s++) {
+      mbar_init(&full_a[s], kGatherWarps * 32);
+      mbar_init(&full_b[s], 1);
+      mbar_init(&empty[s], 1);
+      mbar_init(&meta_full[s], 1);
+    }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], kEpiWarps * 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)C::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < kEpiWarps) {
+    // =========================== epilogue ===========================
+    float sc[COUT], sh[COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; c++) {
+      sc[c] = scale ? __ldg(&scale[c]) : 1.0f;
+      sh[c] = shift ? __ldg(&shift[c]) : 0.0f;
+    }
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+      const int a = it & 1;
+      mbar_wait(&acc_full[a], (it >> 1) & 1);
+      tc_fence_after();
+      const int row = tile * kTileM + warp * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * COUT);
+      float* orow = out + (size_t)row * COUT;
+#pragma unroll
+      for (int c0 = 0; c0 < COUT; c0 += 16) {
+        uint32_t v[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
+            "%14, %15}, [%16];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(taddr + (uint32_t)c0));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c0 + 16 >= COUT) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&acc_empty[a]);
+        }
+        if (row < n_out) {
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            float4 o;
+            o.x = fmaf(__uint_as_float(v[4 * q + 0]), sc[c0 + 4 * q + 0], sh[c0 + 4 * q + 0]);
+            o.y = fmaf(__uint_as_float(v[4 * q + 1]), sc[c0 + 4 * q + 1], sh[c0 + 4 * q + 1]);
+            o.z = fmaf(__uint_as_float(v[4 * q + 2]), sc[c0 + 4 * q + 2], sh[c0 + 4 * q + 2]);
+            o.w = fmaf(__uint_as_float(v[4 * q + 3]), sc[c0 + 4 * q + 3], sh[c0 + 4 * q + 3]);
+            if (relu) {
+              o.x = fmaxf(o.x, 0.f);
+              o.y = fmaxf(o.y, 0.f);
+              o.z = fmaxf(o.z, 0.f);
+              o.w = fmaxf(o.w, 0.f);
+            }
+            *reinterpret_cast<float4*>(orow + c0 + 4 * q) = o;
+          }
+        }
+      }
+    }
+  } else if (warp == kEpiWarps) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kTileM, COUT);
+      uint32_t slot = 0, ph = 0;
+      int it = 0;
+      bool done = false;
+      while (!done) {
+        const int a = it & 1;
+        bool first = true, tile_open = false;
+        while (true) {
+          mbar_wait(&full_a[slot], ph);
+          const SlotMeta m = meta[slot];
+          if (m.kk < 0) {
+            done = true;
+            break;
+          }
+          if (!tile_open) {  // first slot of a tile: the accumulator buffer must have been drained
+            mbar_wait(&acc_empty[a], ((it >> 1) & 1) ^ 1);
+            tile_open = true;
+          }
+          mbar_wait(&full_b[slot], ph);
+          tc_fence_after();
+          unsigned char* st = stages + (size_t)slot * C::kStageBytes;
+          const uint32_t a_hi = smem_u32(st), a_lo = a_hi + C::kAPartBytes;
+          const uint32_t b_hi = a_hi + C::kABytes, b_lo = b_hi + C::kBPartBytes;
+          const uint32_t d = tmem_base + (uint32_t)(a * COUT);
+#pragma unroll
+          for (int ks = 0; ks < C::kKSteps; ks++) {
+            const uint32_t ao = (uint32_t)(ks >> 2) * C::kAChunkBytes + (uint32_t)(ks & 3) * 32u;
+            const uint32_t bo = (uint32_t)(ks >> 2) * C::kBChunkBytes + (uint32_t)(ks & 3) * 32u;
+            const uint64_t dah = make_desc(a_hi + ao), dal = make_desc(a_lo + ao);
+            const uint64_t dbh = make_desc(b_hi + bo), dbl = make_desc(b_lo + bo);
+            umma_tf32(d, dal, dbh, idesc, first ? 0u : 1u);  // small terms first
+            first = false;
+            umma_tf32(d, dah, dbl, idesc, 1u);
+            umma_tf32(d, dah, dbh, idesc, 1u);
+          }
+          umma_commit(&empty[slot]);  // slot reusable once these MMAs have read it
+          const int last = m.last;
+          if (last) umma_commit(&acc_full[a]);
+          if (++slot == C::kStages) {
+            slot = 0;
+            ph ^= 1;
+          }
+          if (last) break;
+        }
+        it++;
+      }
+    }
+  } else if (warp == kEpiWarps + 1) {
+    // =========================== weight loader (1-D TMA) ===========================
+    if (lane == 0) {
+      uint32_t slot = 0, ph = 0;
+      while (true) {
+        mbar_wait(&meta_full[slot], ph);
+        const int kk = meta[slot].kk;
+        if (kk < 0) break;
+        unsigned char* st = stages + (size_t)slot * C::kStageBytes;
+        mbar_arrive_expect_tx(&full_b[slot], (uint32_t)C::kBBytes);
+        bulk_g2s(st + C::kABytes, wprep + (size_t)kk * C::kBBytes, (uint32_t)C::kBBytes, &full_b[slot]);
+        if (++slot == C::kStages) {
+          slot = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else {
+    // =========================== gatherers ===========================
+    const int gt = tid - 32 * (kEpiWarps + 2);  // 0..127
+    constexpr int NG = kGatherWarps * 32;
+    uint32_t slot = 0, ph = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int row0 = tile * kTileM;
+      // the tile's rule rows for every offset (coalesced) + which offsets are used at all
+      asm volatile("bar.sync 1, %0;" ::"n"(NG) : "memory");  // previous tile's idx_tile readers are done
+      if (gt == 0) *tile_mask = 0u;
+      asm volatile("bar.sync 1, %0;" ::"n"(NG) : "memory");
+      {
+        const int o = row0 + gt;
+        uint32_t mine = 0;
+        for (int kk = 0; kk < KV; kk++) {
+          const int v = o < n_out ? __ldg(&nbr[(size_t)kk * nbr_stride + o]) : -1;
+          idx_tile[kk * kTileM + gt] = v;
+          const uint32_t any = __ballot_sync(0xffffffffu, v >= 0);
+          if (any) mine |= 1u << kk;
+        }
+        if (lane == 0 && mine) atomicOr(tile_mask, mine);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(NG) : "memory");
+      uint32_t mask = *tile_mask;
+      if (mask == 0) mask = 1u;  // cannot happen for a well-formed rule book; keeps the protocol total
+      while (mask) {
+        const int kk = __ffs(mask) - 1;
+        mask &= mask - 1;
+        mbar_wait(&empty[slot], ph ^ 1);
+        if (gt == 0) {
+          meta[slot].kk = kk;
+          meta[slot].last = (mask == 0);
+          mbar_arrive(&meta_full[slot]);  // weight loader may start (release orders the meta writes)
+        }
+        unsigned char* st = stages + (size_t)slot * C::kStageBytes;
+        const int* idx = idx_tile + kk * kTileM;
+        constexpr int UPR = C::kUnitsPerRow;
+        constexpr int ITEMS = kTileM * UPR / NG;  // float4 units per thread
+        float4 v[ITEMS];
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+          const int u = i * NG + gt;
+          const int r = u / UPR, j = u % UPR;
+          const int src = idx[r];
+          v[i] = src >= 0 ? __ldg(reinterpret_cast<const float4*>(feat + (size_t)src * CIN) + j)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+          const int u = i * NG + gt;
+          const int r = u / UPR, j = u % UPR;
+          const uint32_t off = (uint32_t)(j >> 3) * C::kAChunkBytes + (uint32_t)(r >> 3) * 1024u +
+                               (uint32_t)(r & 7) * 128u + (uint32_t)(((j & 7) ^ (r & 7)) << 4);
+          float4 hi, lo;
+          hi.x = __uint_as_float(__float_as_uint(v[i].x) & 0xFFFFE000u);
+          hi.y = __uint_as_float(__float_as_uint(v[i].y) & 0xFFFFE000u);
+          hi.z = __uint_as_float(__float_as_uint(v[i].z) & 0xFFFFE000u);
+          hi.w = __uint_as_float(__float_as_uint(v[i].w) & 0xFFFFE000u);
+          lo.x = v[i].x - hi.x;
+          lo.y = v[i].y - hi.y;
+          lo.z = v[i].z - hi.z;
+          lo.w = v[i].w - hi.w;
+          *reinterpret_cast<float4*>(st + off) = hi;
+          *reinterpret_cast<float4*>(st + C::kAPartBytes + off) = lo;
+        }
+        fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+        mbar_arrive(&full_a[slot]);
+        if (++slot == C::kStages) {
+          slot = 0;
+          ph ^= 1;
+        }
+      }
+    }
+    // termination slot
+    mbar_wait(&empty[slot], ph ^ 1);
+    if (gt == 0) {
+      meta[slot].kk = -1;
+      meta[slot].last = 1;
+      mbar_arrive(&meta_full[slot]);
+    }
+    mbar_arrive(&full_a[slot]);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::kTmemCols)
+                 : "memory");
+  }
+}
+
+// One-time weight preparation: (KV, Cin, Cout) fp32 -> per kk the exact shared-memory image the kernel
+// consumes: [hi | lo] x chunks x (COUT rows x 128 B), K-major, 128B-swizzled, tf32-split.
+__global__ void prepare_weights_kernel(const float* __restrict__ w, int KV, int Cin, int Cout,
+                                       unsigned char* __restrict__ img) {
+  const int chunks = (Cin + 31) / 32;
+  const size_t part = (size_t)chunks * Cout * 128, per_kk = 2 * part;
+  const int total = KV * Cout * chunks * 32;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int kl = e % 32;
+    int t = e / 32;
+    const int n = t % Cout;
+    t /= Cout;
+    const int ch = t % chunks, kk = t / chunks;
+    const int k = ch * 32 + kl;
+    const float v = k < Cin ? w[((size_t)kk * Cin + k) * Cout + n] : 0.f;
+    const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    const float lo = v - hi;
+    const size_t off = (size_t)ch * Cout * 128 + (size_t)(n >> 3) * 1024 + (size_t)(n & 7) * 128 +
+                       (size_t)((((kl >> 2) ^ (n & 7)) << 4) + (kl & 3) * 4);
+    *reinterpret_cast<float*>(img + (size_t)kk * per_kk + off) = hi;
+    *reinterpret_cast<float*>(img + (size_t)kk * per_kk + part + off) = lo;
+  }
+}
+
+template <int CIN, int COUT>
+int launch_tc(const float* feat, const unsigned char* wprep, const int* nbr, int nbr_stride, const int* n_out,
+              int out_cap, int KV, const float* scale, const float* shift, int relu, float* out, cudaStream_t st) {
+  using C = TcCfg<CIN, COUT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    V3D_CUDA_TRY(cudaFuncSetAttribute(sparse_conv_tc_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)C::kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles_cap = ceil_div(out_cap, kTileM);
+  const int grid = tiles_cap < kNumSMs ? (tiles_cap > 0 ? tiles_cap : 1) : kNumSMs;
+  sparse_conv_tc_kernel<CIN, COUT><<<grid, kThreads, C::kSmemBytes, st>>>(feat, wprep, nbr, nbr_stride, n_out, out_cap,
+                                                                         KV, scale, shift, relu, out);
+  return check_launch();
+}
+
+inline bool tc_supported(int KV, int Cin, int Cout) {
+  return KV <= kMaxKV && (Cin == 16 || Cin == 32 || Cin == 64) && (Cout == 16 || Cout == 32 || Cout == 64);
+}
+
+}  // namespace
+}  // namespace v3d
+
+using namespace v3d;
+
+extern "C" size_t v3d_sparse_conv_prepared_bytes(int kernel_volume, int Cin, int Cout) {
+  if (!tc_supported(kernel_volume, Cin, Cout)) return 0;  // 0 = this shape runs on the exact-fp32 SIMT path
+  return (size_t)kernel_volume * 2 * ((Cin + 31) / 32) * Cout * 128;
+}
+
+extern "C" int v3d_sparse_conv_prepare(const float* weight, int kernel_volume, int Cin, int Cout, void* prepared,
+                                       size_t prepared_bytes, v3d_stream_t stream) {
+  if (!weight || !prepared) return V3D_ERR_INVALID_ARGUMENT;
+  const size_t need = v3d_sparse_conv_prepared_bytes(kernel_volume, Cin, Cout);
+  if (need == 0) return V3D_ERR_INVALID_ARGUMENT;
+  if (prepared_bytes < need) return V3D_ERR_WORKSPACE_TOO_SMALL;
+  const int total = kernel_volume * Cout * ((Cin + 31) / 32) * 32;
+  prepare_weights_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(
+      weight, kernel_volume, Cin, Cout, static_cast<unsigned char*>(prepared));
+  return check_launch();
+}
+
+extern "C" int v3d_sparse_conv_fwd_tc(const float* feat, const void* prepared, const int* nbr, int nbr_stride,
+                                      const int* n_out, int out_capacity, int kernel_volume, int Cin, int Cout,
+                                      const float* scale, const float* shift, int relu, float* out,
+                                      v3d_stream_t stream) {
+  if (!feat || !prepared || !nbr || !n_out || !out) return V3D_ERR_INVALID_ARGUMENT;
+  if (out_capacity <= 0 || kernel_volume <= 0 || nbr_stride < out_capacity) return V3D_ERR_INVALID_ARGUMENT;
+  if ((scale == nullptr) != (shift == nullptr)) return V3D_ERR_INVALID_ARGUMENT;
+  if (!tc_supported(kernel_volume, Cin, Cout)) return V3D_ERR_INVALID_ARGUMENT;
+  if ((reinterpret_cast<uintptr_t>(prepared) & 15) || (reinterpret_cast<uintptr_t>(feat) & 15))
+    return V3D_ERR_INVALID_ARGUMENT;
+  const unsigned char* wp = static_cast<const unsigned char*>(prepared);
+  cudaStream_t st = as_stream(stream);
+#define V3D_TC_CASE(CI, CO)                                                                                       \
+  if (Cin == CI && Cout == CO)                                                                                    \
+    return launch_tc<CI, CO>(feat, wp, nbr, nbr_stride, n_out, out_capacity, kernel_volume, scale, shift, relu, out, st);
+  V3D_TC_CASE(16, 16)
+  V3D_TC_CASE(16, 32)
+  V3D_TC_CASE(16, 64)
+  V3D_TC_CASE(32, 32)
+  V3D_TC_CASE(32, 64)
+  V3D_TC_CASE(64, 64)
+  V3D_TC_CASE(32, 16)
+  V3D_TC_CASE(64, 32)
+  V3D_TC_CASE(64, 16)
+#undef V3D_TC_CASE
+  return V3D_ERR_INVALID_ARGUMENT;
+}

@@ -236,8 +236,41 @@ def rulebook_conv(in_table, indices, n_rows, batch_size, shape, ksize, stride, p
     return out_indices, n_out, nbr, out_shape
 
 
+class PreparedWeights:
+    """Per-layer weight image for the tcgen05 path (hi/lo tf32 split, K-major, 128B-swizzled), built once.
+    `.buf` is None when the shape is only supported by the exact-fp32 SIMT path (e.g. Cin = 4)."""
+
+    def __init__(self, weight):
+        self.cin, self.cout = int(weight.shape[-2]), int(weight.shape[-1])
+        self.kv = weight.numel() // (self.cin * self.cout)
+        w = weight.detach().reshape(self.kv, self.cin, self.cout).contiguous().float()
+        self.weight = w
+        nbytes = _lib.load().v3d_sparse_conv_prepared_bytes(self.kv, self.cin, self.cout)
+        self.buf = None
+        if nbytes:
+            self.buf = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+            with torch.cuda.device(w.device):
+                check(_lib.load().v3d_sparse_conv_prepare(w.data_ptr(), self.kv, self.cin, self.cout,
+                                                          self.buf.data_ptr(), nbytes, _stream()),
+                      "v3d_sparse_conv_prepare")
+
+
 def sparse_conv(feat, weight, nbr, n_out, out_capacity, scale=None, shift=None, relu=False, out=None):
-    """feat (rows, Cin); weight (KV, Cin, Cout) or spconv's (k0,k1,k2,Cin,Cout); nbr (KV, stride)."""
+    """feat (rows, Cin); weight (KV, Cin, Cout) / spconv's (k0,k1,k2,Cin,Cout) -> exact-fp32 SIMT kernel,
+    or a PreparedWeights -> tcgen05 3xTF32 kernel when the shape supports it; nbr (KV, stride)."""
+    if isinstance(weight, PreparedWeights):
+        pw = weight
+        if out is None:
+            out = torch.empty((out_capacity, pw.cout), dtype=_F32, device=feat.device)
+        if pw.buf is not None:
+            with torch.cuda.device(feat.device):
+                check(_lib.load().v3d_sparse_conv_fwd_tc(
+                    feat.data_ptr(), pw.buf.data_ptr(), nbr.data_ptr(), nbr.shape[1], n_out.data_ptr(),
+                    int(out_capacity), pw.kv, pw.cin, pw.cout, scale.data_ptr() if scale is not None else None,
+                    shift.data_ptr() if shift is not None else None, int(bool(relu)), out.data_ptr(), _stream()),
+                    "v3d_sparse_conv_fwd_tc")
+            return out
+        weight = pw.weight
     cin, cout = weight.shape[-2], weight.shape[-1]
     kv = weight.numel() // (cin * cout)
     if out is None:

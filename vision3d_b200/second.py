@@ -297,7 +297,7 @@ def _fold_bn(bn):
 
 class SecondEngine:
     def __init__(self, model: SecondB200, batch_size: int, points_capacity: int, device, level_caps=None,
-                 use_graph=True, cap_policy=0, frame_points_capacity=None):
+                 use_graph=True, cap_policy=0, frame_points_capacity=None, tensor_cores=True):
         cfg = model.cfg
         self.cfg, self.B, self.P = cfg, int(batch_size), int(points_capacity)
         self.dev = torch.device(device)
@@ -332,6 +332,8 @@ class SecondEngine:
                 conv, bn = seq[0], seq[1]
                 scale, shift = _fold_bn(bn)
                 w = conv.weight.detach().reshape(-1, conv.in_channels, conv.out_channels).contiguous().float()
+                if tensor_cores:  # tcgen05 3xTF32 path where the shape supports it (Cin >= 16), else exact fp32
+                    w = ops.PreparedWeights(w)
                 d = dict(kind=l[0], w=w, scale=scale, shift=shift, cin=conv.in_channels, cout=conv.out_channels,
                          level_in=b, ks=conv.kernel_size, stride=conv.stride, pad=conv.padding, dil=conv.dilation)
                 if l[0] == "conv":
@@ -369,6 +371,8 @@ class SecondEngine:
         self.c_idx = torch.arange(n_cls, device=dev)[None, :, None].expand(B, -1, cfg.TOPK).reshape(-1).contiguous()
         self.g_idx = (self.c_idx + n_cls * self.b_idx).contiguous()
         self.thr = torch.tensor([a["score_thresh"] for a in cfg.ANCHORS], dtype=torch.float32, device=dev)
+        self.bev_cols = torch.tensor([0, 1, 3, 4, 6], device=dev)  # x, y, w, l, yaw (proposal.py:52)
+        self.row_ids = torch.arange(self.N, device=dev)
         # packed result: 7 box + score + batch + class + valid, then one row of counters
         self.result = torch.zeros((self.N + 1, 11), dtype=torch.float32, device=dev)
         self.h_result = torch.zeros((self.N + 1, 11), dtype=torch.float32).pin_memory()
@@ -430,7 +434,7 @@ class SecondEngine:
         cfg = self.cfg
         boxes, scores = self.model.head.candidates(self._fmap, self.anchors)
         self._scores, self._boxes = scores.reshape(-1), boxes.reshape(-1, cfg.BOX_DOF)
-        self._nms_in = group_offsets(self._boxes[:, [0, 1, 3, 4, 6]], self.g_idx)
+        self._nms_in = group_offsets(self._boxes.index_select(1, self.bev_cols), self.g_idx)
 
     def _nms(self):
         self.keep.zero_()
@@ -439,7 +443,7 @@ class SecondEngine:
     def _pack(self):
         k = self.keep
         ks, kc = self._scores[k], self.c_idx[k]
-        valid = (ks > self.thr[kc]) & (torch.arange(self.N, device=self.dev) < self.count)
+        valid = (ks > self.thr[kc]) & (self.row_ids < self.count)
         r = self.result
         r[:self.N, :7] = self._boxes[k]
         r[:self.N, 7] = ks
