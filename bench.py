@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=16, help="frames per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--rpn", default="fused", choices=["module", "fused", "fused_nhwc"])
     ap.add_argument("--simt", action="store_true", help="exact-fp32 SIMT sparse conv instead of tcgen05 3xTF32")
     return ap.parse_args()
 
@@ -214,7 +215,7 @@ def run_b200(args):
     cfg = second.car_config()
     model = second.init_for_benchmark(second.SecondB200(cfg), 0)
     eng = second.SecondEngine(model, B, B * PTS_PER_FRAME, dev, use_graph=not args.no_graph,
-                              tensor_cores=not args.simt).capture()
+                              tensor_cores=not args.simt, rpn_mode=args.rpn).capture()
 
     # distinct synthetic batches per rank, staged in pinned host memory and mirrored on the device
     n_sets = 4
@@ -337,8 +338,8 @@ def run_b200(args):
                              % (eng.dense_out.numel() * 4 / 1e6),
                        "cuda_graph": eng.graph is not None,
                        "sparse_conv": "exact-fp32 SIMT" if args.simt else "tcgen05 kind::tf32 3xTF32 (Cin>=16), "
-                                                                          "exact-fp32 SIMT (Cin=4)", "rpn": "torch/cuDNN fp32 (TF32 allowed=%s)"
-                                                                   % torch.backends.cudnn.allow_tf32,
+                                                                          "exact-fp32 SIMT (Cin=4)", "rpn": "torch/cuDNN fp32 (TF32 allowed=%s), mode=%s"
+                                                                   % (torch.backends.cudnn.allow_tf32, args.rpn),
                        "active_sites_per_level": rows, "detections": int(counts["kept"])},
             "e2e": {"value": round(e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": eng.h2d_bytes(),
                     "d2h_bytes_per_step": eng.d2h_bytes() * world, "ms_per_step": round(ms_e2e / args.steps, 4)},

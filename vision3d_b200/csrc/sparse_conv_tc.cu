@@ -9,10 +9,13 @@
 //                           frees the slot / publishes the accumulator through mbarriers
 //   warp  5    weight TMA : one thread; cp.async.bulk (1-D TMA) of the pre-swizzled, pre-split W[kk]
 //                           image (hi+lo) into the slot, completion on the slot's mbarrier
-//   warps 6-9  gatherers  : stage the tile's rule rows (all KV offsets x 128 outputs), skip offsets
-//                           no row of the tile uses, gather the neighbour feature rows with 128-bit
-//                           loads, split every value into tf32 hi / lo parts and write them into
-//                           the 128B-swizzled K-major UMMA layout
+//   warps 6-13 gatherers  : two independent groups of 4 warps, pipeline slot q belongs to group q % 2.
+//                           A group stages the tile's rule rows (all KV offsets x 128 outputs), skips
+//                           offsets no row of the tile uses, gathers the neighbour feature rows with
+//                           128-bit loads issued up to kDepth slots AHEAD into registers (the load
+//                           latency overlaps the MMAs of earlier slots and the other group's work),
+//                           then splits every value into tf32 hi / lo parts and writes them into the
+//                           128B-swizzled K-major UMMA layout once the slot is free
 // Output rows are written exactly once (no atomics, deterministic). Arithmetic: every product is
 // exact in fp32 (11-bit x 11-bit mantissas); dropping only a_lo*b_lo bounds the relative error of a
 // product by ~2^-21, far inside the 1e-4 the contract allows.
@@ -26,8 +29,8 @@ namespace v3d {
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kEpiWarps = 4, kGatherWarps = 4;
-constexpr int kThreads = 32 * (kEpiWarps + 2 + kGatherWarps);  // 320
+constexpr int kEpiWarps = 4, kGatherWarps = 4, kGatherGroups = 2;
+constexpr int kThreads = 32 * (kEpiWarps + 2 + kGatherWarps * kGatherGroups);  // 448
 constexpr int kMaxKV = 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -107,9 +110,12 @@ struct TcCfg {
   static constexpr int kBBytes = 2 * kBPartBytes;                   // == one prepared W[kk] image
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (CIN >= 64) ? 2 : 3;
+  static constexpr int kItems = kTileM * kUnitsPerRow / (kGatherWarps * 32);  // float4 loads per thread and slot
+  static constexpr int kDepth = kItems >= 16 ? 1 : (kItems >= 8 ? 2 : 4);     // register sets (slots in flight)
   static constexpr int kTmemCols = (2 * COUT <= 32) ? 32 : (2 * COUT <= 64 ? 64 : (2 * COUT <= 128 ? 128 : 256));
   static constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * kStageBytes +
-                                       sizeof(int) * kMaxKV * kTileM + 1024 /*barriers + meta*/;
+                                       sizeof(int) * kGatherGroups * kMaxKV * kTileM +
+                                       1024 /*barriers + meta*/ + 2 * COUT * sizeof(float);
 };
 
 struct SlotMeta {
@@ -127,8 +133,8 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* stages = base;                                             // kStages x (A_hi A_lo B_hi B_lo)
-  int* idx_tile = reinterpret_cast<int*>(base + (size_t)C::kStages * C::kStageBytes);  // [KV][128]
-  unsigned char* tail = reinterpret_cast<unsigned char*>(idx_tile + kMaxKV * kTileM);
+  int* idx_tile = reinterpret_cast<int*>(base + (size_t)C::kStages * C::kStageBytes);  // [group][KV][128]
+  unsigned char* tail = reinterpret_cast<unsigned char*>(idx_tile + kGatherGroups * kMaxKV * kTileM);
   uint64_t* full_a = reinterpret_cast<uint64_t*>(tail);          // [kStages]
   uint64_t* full_b = full_a + 4;
   uint64_t* empty = full_b + 4;
@@ -137,7 +143,9 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
   uint64_t* acc_empty = acc_full + 2;   // [2]
   SlotMeta* meta = reinterpret_cast<SlotMeta*>(acc_empty + 2);  // [kStages]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(meta + 4);
-  uint32_t* tile_mask = tmem_slot + 1;
+  uint32_t* tile_mask = tmem_slot + 1;  // [kGatherGroups]
+  float* s_scale = reinterpret_cast<float*>(tail + 1024);
+  float* s_shift = s_scale + COUT;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_out = min(*n_out_ptr, out_cap);
@@ -145,7 +153,7 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
 
   if (tid == 0) {
     for (int s = 0; s < C::kStages; s++) {
-      mbar_init(&full_a[s], kGatherWarps * 32);
+      mbar_init(&full_a[s], kGatherWarps * 32);  // the one group that owns the slot
       mbar_init(&full_b[s], 1);
       mbar_init(&empty[s], 1);
       mbar_init(&meta_full[s], 1);
@@ -155,6 +163,10 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
       mbar_init(&acc_empty[a], kEpiWarps * 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int c = tid; c < COUT; c += kThreads) {
+    s_scale[c] = scale ? __ldg(&scale[c]) : 1.0f;
+    s_shift[c] = shift ? __ldg(&shift[c]) : 0.0f;
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -169,12 +181,8 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
 
   if (warp < kEpiWarps) {
     // =========================== epilogue ===========================
-    float sc[COUT], sh[COUT];
-#pragma unroll
-    for (int c = 0; c < COUT; c++) {
-      sc[c] = scale ? __ldg(&scale[c]) : 1.0f;
-      sh[c] = shift ? __ldg(&shift[c]) : 0.0f;
-    }
+    const float* sc = s_scale;
+    const float* sh = s_shift;
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
       const int a = it & 1;
@@ -285,51 +293,92 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
     }
   } else {
     // =========================== gatherers ===========================
-    const int gt = tid - 32 * (kEpiWarps + 2);  // 0..127
     constexpr int NG = kGatherWarps * 32;
-    uint32_t slot = 0, ph = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int row0 = tile * kTileM;
-      // the tile's rule rows for every offset (coalesced) + which offsets are used at all
-      asm volatile("bar.sync 1, %0;" ::"n"(NG) : "memory");  // previous tile's idx_tile readers are done
-      if (gt == 0) *tile_mask = 0u;
-      asm volatile("bar.sync 1, %0;" ::"n"(NG) : "memory");
-      {
-        const int o = row0 + gt;
-        uint32_t mine = 0;
-        for (int kk = 0; kk < KV; kk++) {
-          const int v = o < n_out ? __ldg(&nbr[(size_t)kk * nbr_stride + o]) : -1;
-          idx_tile[kk * kTileM + gt] = v;
-          const uint32_t any = __ballot_sync(0xffffffffu, v >= 0);
-          if (any) mine |= 1u << kk;
+    constexpr int UPR = C::kUnitsPerRow, ITEMS = C::kItems, DEPTH = C::kDepth;
+    const int gtid = tid - 32 * (kEpiWarps + 2);
+    const int grp = gtid / NG, gt = gtid % NG;
+    int* idx_g = idx_tile + grp * kMaxKV * kTileM;
+    uint32_t* mask_g = tile_mask + grp;
+
+    // Cursor over the CTA's sequence of non-empty (tile, offset) slots; every group walks the whole
+    // sequence (so slot numbers agree) and keeps the slots with q % kGatherGroups == grp.
+    int cur_tile = (int)blockIdx.x - (int)gridDim.x;
+    uint32_t cur_mask = 0, q_next = 0;
+    auto next_item = [&](int& kk, int& last, uint32_t& q) -> bool {
+      while (true) {
+        while (cur_mask) {
+          kk = __ffs(cur_mask) - 1;
+          cur_mask &= cur_mask - 1;
+          q = q_next++;
+          if ((int)(q % kGatherGroups) == grp) {
+            last = (cur_mask == 0);
+            return true;
+          }
         }
-        if (lane == 0 && mine) atomicOr(tile_mask, mine);
+        cur_tile += gridDim.x;
+        if (cur_tile >= n_tiles) return false;
+        // stage this tile's rule rows (group-private copy) and find the offsets it uses
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(NG) : "memory");  // loads that used idx_g are issued
+        if (gt == 0) *mask_g = 0u;
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(NG) : "memory");
+        const int o = cur_tile * kTileM + gt;
+        uint32_t mine = 0;
+        for (int k2 = 0; k2 < KV; k2++) {
+          const int v = o < n_out ? __ldg(&nbr[(size_t)k2 * nbr_stride + o]) : -1;
+          idx_g[k2 * kTileM + gt] = v;
+          if (__ballot_sync(0xffffffffu, v >= 0)) mine |= 1u << k2;
+        }
+        if (lane == 0 && mine) atomicOr(mask_g, mine);
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(NG) : "memory");
+        cur_mask = *mask_g;
+        if (cur_mask == 0) cur_mask = 1u;  // cannot happen for a well-formed rule book; keeps the protocol total
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(NG) : "memory");
-      uint32_t mask = *tile_mask;
-      if (mask == 0) mask = 1u;  // cannot happen for a well-formed rule book; keeps the protocol total
-      while (mask) {
-        const int kk = __ffs(mask) - 1;
-        mask &= mask - 1;
-        mbar_wait(&empty[slot], ph ^ 1);
+    };
+
+    float4 v[DEPTH][ITEMS];
+    int it_kk[DEPTH], it_last[DEPTH];
+    uint32_t it_q[DEPTH];
+    bool it_ok[DEPTH];
+    auto issue = [&](int d) {
+      it_ok[d] = next_item(it_kk[d], it_last[d], it_q[d]);
+      if (!it_ok[d]) return;
+      const int* idx = idx_g + it_kk[d] * kTileM;
+#pragma unroll
+      for (int i = 0; i < ITEMS; i++) {
+        const int u = i * NG + gt;
+        const int r = u / UPR, j = u % UPR;
+        const int src = idx[r];
+        v[d][i] = src >= 0 ? __ldg(reinterpret_cast<const float4*>(feat + (size_t)src * CIN) + j)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+#pragma unroll
+    for (int d = 0; d < DEPTH; d++) it_ok[d] = false;
+#pragma unroll
+    for (int d = 0; d < DEPTH; d++) {
+      bool prev_ok = true;
+#pragma unroll
+      for (int e = 0; e < d; e++) prev_ok = prev_ok && it_ok[e];
+      if (prev_ok) issue(d);
+    }
+    bool running = true;
+    while (running) {
+#pragma unroll
+      for (int d = 0; d < DEPTH; d++) {
+        if (!running) break;
+        if (!it_ok[d]) {
+          running = false;
+          break;
+        }
+        const uint32_t q = it_q[d];
+        const uint32_t slot = q % C::kStages, use = q / C::kStages;
+        mbar_wait(&empty[slot], (use & 1u) ^ 1u);
         if (gt == 0) {
-          meta[slot].kk = kk;
-          meta[slot].last = (mask == 0);
+          meta[slot].kk = it_kk[d];
+          meta[slot].last = it_last[d];
           mbar_arrive(&meta_full[slot]);  // weight loader may start (release orders the meta writes)
         }
         unsigned char* st = stages + (size_t)slot * C::kStageBytes;
-        const int* idx = idx_tile + kk * kTileM;
-        constexpr int UPR = C::kUnitsPerRow;
-        constexpr int ITEMS = kTileM * UPR / NG;  // float4 units per thread
-        float4 v[ITEMS];
-#pragma unroll
-        for (int i = 0; i < ITEMS; i++) {
-          const int u = i * NG + gt;
-          const int r = u / UPR, j = u % UPR;
-          const int src = idx[r];
-          v[i] = src >= 0 ? __ldg(reinterpret_cast<const float4*>(feat + (size_t)src * CIN) + j)
-                          : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
 #pragma unroll
         for (int i = 0; i < ITEMS; i++) {
           const int u = i * NG + gt;
@@ -337,33 +386,33 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
           const uint32_t off = (uint32_t)(j >> 3) * C::kAChunkBytes + (uint32_t)(r >> 3) * 1024u +
                                (uint32_t)(r & 7) * 128u + (uint32_t)(((j & 7) ^ (r & 7)) << 4);
           float4 hi, lo;
-          hi.x = __uint_as_float(__float_as_uint(v[i].x) & 0xFFFFE000u);
-          hi.y = __uint_as_float(__float_as_uint(v[i].y) & 0xFFFFE000u);
-          hi.z = __uint_as_float(__float_as_uint(v[i].z) & 0xFFFFE000u);
-          hi.w = __uint_as_float(__float_as_uint(v[i].w) & 0xFFFFE000u);
-          lo.x = v[i].x - hi.x;
-          lo.y = v[i].y - hi.y;
-          lo.z = v[i].z - hi.z;
-          lo.w = v[i].w - hi.w;
+          hi.x = __uint_as_float(__float_as_uint(v[d][i].x) & 0xFFFFE000u);
+          hi.y = __uint_as_float(__float_as_uint(v[d][i].y) & 0xFFFFE000u);
+          hi.z = __uint_as_float(__float_as_uint(v[d][i].z) & 0xFFFFE000u);
+          hi.w = __uint_as_float(__float_as_uint(v[d][i].w) & 0xFFFFE000u);
+          lo.x = v[d][i].x - hi.x;
+          lo.y = v[d][i].y - hi.y;
+          lo.z = v[d][i].z - hi.z;
+          lo.w = v[d][i].w - hi.w;
           *reinterpret_cast<float4*>(st + off) = hi;
           *reinterpret_cast<float4*>(st + C::kAPartBytes + off) = lo;
         }
         fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
         mbar_arrive(&full_a[slot]);
-        if (++slot == C::kStages) {
-          slot = 0;
-          ph ^= 1;
-        }
+        issue(d);  // refill this register set: loads fly while the other sets / the other group are processed
       }
     }
-    // termination slot
-    mbar_wait(&empty[slot], ph ^ 1);
-    if (gt == 0) {
-      meta[slot].kk = -1;
-      meta[slot].last = 1;
-      mbar_arrive(&meta_full[slot]);
+    // termination slot: sequence number = total slot count, posted by the group that owns it
+    if ((int)(q_next % kGatherGroups) == grp) {
+      const uint32_t slot = q_next % C::kStages, use = q_next / C::kStages;
+      mbar_wait(&empty[slot], (use & 1u) ^ 1u);
+      if (gt == 0) {
+        meta[slot].kk = -1;
+        meta[slot].last = 1;
+        mbar_arrive(&meta_full[slot]);
+      }
+      mbar_arrive(&full_a[slot]);
     }
-    mbar_arrive(&full_a[slot]);
   }
 
   tc_fence_before();
