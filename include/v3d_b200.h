@@ -182,6 +182,13 @@ V3D_API int v3d_sparse_to_dense(const float* feat, const int* indices, const int
                                 int capacity_rows, int C, int B, const int* shape_host, float* out,
                                 void* workspace, size_t workspace_bytes, v3d_stream_t stream);
 
+/* Same scatter, but written as the BEV map the RPN consumes, in channels-last memory:
+ * out (B, H, W, C*D) with channel index c*D + d == `dense().view(B, C*D, H, W)` (sparse_cnn.py:131-132)
+ * in torch's channels_last format. C must divide 256, D <= 8. */
+V3D_API int v3d_sparse_to_dense_nhwc(const float* feat, const int* indices, const int* n_rows,
+                                     int capacity_rows, int C, int B, const int* shape_host, float* out,
+                                     void* workspace, size_t workspace_bytes, v3d_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * a7  furthest_point_sample(xyz[B,N,3], m) -> idx[B,m] int32   (detector/model.py:53)
  * a8  gather_operation(feat[B,C,N], idx[B,m]) -> [B,C,m]          (detector/model.py:54)

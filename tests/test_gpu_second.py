@@ -179,3 +179,29 @@ def test_c_ext_and_searchsorted_shims(cuda):
     a = torch.tensor([[0, 0, 1, 1, 1, 3]], dtype=torch.int32, device=cuda)
     v = torch.arange(5, dtype=torch.int32, device=cuda)[None]
     assert torchsearchsorted.searchsorted(a, v).tolist() == [[0, 2, 5, 5, 6]]
+
+
+def test_bev_nhwc_matches_dense_and_engine_modes_agree(cuda, no_tf32):
+    """The channels-last BEV writer == dense().view(B, C*D, H, W); engine results do not depend on the RPN
+    execution mode (module / BN-folded fused / fused channels_last)."""
+    from vision3d_b200 import ops
+    rng = np.random.default_rng(0)
+    shape, B, C = [2, 200, 176], 2, 64
+    idx = synth.make_active_sites(3, 6000, shape, B)
+    feat = torch.from_numpy(rng.normal(size=(len(idx), C)).astype(np.float32)).to(cuda)
+    ind = torch.from_numpy(idx).to(cuda)
+    n_rows = torch.tensor([len(idx)], dtype=torch.int32, device=cuda)
+    dense = ops.sparse_to_dense(feat, ind, n_rows, len(idx), B, shape).view(B, C * 2, 200, 176)
+    nhwc = ops.sparse_to_bev_nhwc(feat, ind, n_rows, len(idx), B, shape)
+    assert nhwc.is_contiguous(memory_format=torch.channels_last) and torch.equal(nhwc, dense)
+
+    cfg = second.car_config()
+    model = second.init_for_benchmark(second.SecondB200(cfg), 3)
+    clouds = synth.make_batch(30, 2, 16384)
+    outs = []
+    for mode in ("module", "fused", "fused_nhwc"):
+        eng = second.SecondEngine(model, 2, 2 * 16384, cuda, use_graph=True, rpn_mode=mode).capture()
+        outs.append(eng.infer(clouds))
+    for o in outs[1:]:
+        assert abs(len(o[0]) - len(outs[0][0])) <= 2
+        assert _match(o, outs[0]) >= 0.9 and _match(outs[0], o) >= 0.9

@@ -150,23 +150,39 @@ __global__ void __launch_bounds__(256) conv_mark_kernel(const int4* __restrict__
   const int n = min(*n_rows, cap_rows);
   const int kk = blockIdx.y;
   const int kx = kk % G.ks[2], ky = (kk / G.ks[2]) % G.ks[1], kz = kk / (G.ks[2] * G.ks[1]);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    int4 c = idx[i];
-    int nz = c.y + G.pad[0] - kz * G.dil[0];
-    int ny = c.z + G.pad[1] - ky * G.dil[1];
-    int nx = c.w + G.pad[2] - kx * G.dil[2];
-    if (nz < 0 || ny < 0 || nx < 0) continue;
-    if (nz % G.stride[0] || ny % G.stride[1] || nx % G.stride[2]) continue;
-    int oz = nz / G.stride[0], oy = ny / G.stride[1], ox = nx / G.stride[2];
-    if (oz >= G.out_shape[0] || oy >= G.out_shape[1] || ox >= G.out_shape[2]) continue;
-    unsigned int cell =
-        (unsigned int)((((size_t)c.x * G.out_shape[0] + oz) * G.out_shape[1] + oy) * G.out_shape[2] + ox);
-    unsigned int bit = 1u << (cell & 31);
-    unsigned int old = atomicOr(&W.bitmap[cell >> 5], bit);
-    if (!(old & bit)) {
-      atomicAdd(&W.l1[cell / kCoarse], 1);
-      int u = atomicAdd(W.n_uniq, 1);
-      if (u < out_capacity) W.uniq[u] = cell;
+  const int lane = threadIdx.x & 31;
+  // warp-uniform trip count so that the append below can be aggregated with one atomic per warp
+  for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += gridDim.x * blockDim.x) {
+    const int i = i0 + lane;
+    bool fresh = false;
+    unsigned int cell = 0;
+    if (i < n) {
+      int4 c = idx[i];
+      int nz = c.y + G.pad[0] - kz * G.dil[0];
+      int ny = c.z + G.pad[1] - ky * G.dil[1];
+      int nx = c.w + G.pad[2] - kx * G.dil[2];
+      bool ok = nz >= 0 && ny >= 0 && nx >= 0 && !(nz % G.stride[0]) && !(ny % G.stride[1]) && !(nx % G.stride[2]);
+      int oz = nz / G.stride[0], oy = ny / G.stride[1], ox = nx / G.stride[2];
+      ok = ok && oz < G.out_shape[0] && oy < G.out_shape[1] && ox < G.out_shape[2];
+      if (ok) {
+        cell = (unsigned int)((((size_t)c.x * G.out_shape[0] + oz) * G.out_shape[1] + oy) * G.out_shape[2] + ox);
+        const unsigned int bit = 1u << (cell & 31);
+        const unsigned int old = atomicOr(&W.bitmap[cell >> 5], bit);
+        if (!(old & bit)) {
+          fresh = true;
+          atomicAdd(&W.l1[cell / kCoarse], 1);
+        }
+      }
+    }
+    const unsigned int m = __ballot_sync(0xffffffffu, fresh);
+    if (m) {
+      int base = 0;
+      if (lane == (__ffs(m) - 1)) base = atomicAdd(W.n_uniq, __popc(m));
+      base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+      if (fresh) {
+        const int u = base + __popc(m & ((1u << lane) - 1u));
+        if (u < out_capacity) W.uniq[u] = cell;
+      }
     }
   }
 }

@@ -321,14 +321,29 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
         asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(NG) : "memory");  // loads that used idx_g are issued
         if (gt == 0) *mask_g = 0u;
         asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(NG) : "memory");
+        // all KV loads of this thread are independent: issue them back to back (no warp-level op in
+        // between -- a ballot per load would serialise 27 L2 round trips per tile)
         const int o = cur_tile * kTileM + gt;
-        uint32_t mine = 0;
-        for (int k2 = 0; k2 < KV; k2++) {
-          const int v = o < n_out ? __ldg(&nbr[(size_t)k2 * nbr_stride + o]) : -1;
-          idx_g[k2 * kTileM + gt] = v;
-          if (__ballot_sync(0xffffffffu, v >= 0)) mine |= 1u << k2;
+        {
+          const int* src = nbr + o;
+#pragma unroll 9
+          for (int k2 = 0; k2 < KV; k2++) {
+            const int v = o < n_out ? __ldg(src + (size_t)k2 * nbr_stride) : -1;
+            idx_g[k2 * kTileM + gt] = v;
+          }
         }
-        if (lane == 0 && mine) atomicOr(mask_g, mine);
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(NG) : "memory");
+        {
+          // which offsets does the tile use at all? warp w inspects offsets w, w+4, ...
+          const int w = gt >> 5;
+          uint32_t mine = 0;
+          for (int k2 = w; k2 < KV; k2 += kGatherWarps) {
+            const int* row = idx_g + k2 * kTileM;
+            const bool any = (row[lane] >= 0) | (row[lane + 32] >= 0) | (row[lane + 64] >= 0) | (row[lane + 96] >= 0);
+            if (__any_sync(0xffffffffu, any)) mine |= 1u << k2;
+          }
+          if (lane == 0 && mine) atomicOr(mask_g, mine);
+        }
         asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(NG) : "memory");
         cur_mask = *mask_g;
         if (cur_mask == 0) cur_mask = 1u;  // cannot happen for a well-formed rule book; keeps the protocol total

@@ -150,19 +150,24 @@ __global__ void __launch_bounds__(kChunk) vox_assign_kernel(const float* __restr
   const int start = frame_off[b], n = frame_off[b + 1] - start;
   if (blockIdx.x * kChunk >= n && blockIdx.x > 0) return;
   // frame base = sum over earlier frames of min(openers, max_voxels); chunk prefix inside frame
-  if (threadIdx.x < 32) {
-    int base = 0;
-    for (int f = 0; f <= b; f++) {
-      const int nf = frame_off[f + 1] - frame_off[f];
-      const int nch = f < b ? ceil_div(nf, kChunk) : (int)blockIdx.x;
+  {
+    // thread t owns earlier frame t (all its chunk loads are independent -> one round of latency, not one
+    // per frame), threads also stride over the earlier chunks of this frame; two block reductions
+    int part = 0, cp = 0;
+    for (int f = threadIdx.x; f < b; f += blockDim.x) {
+      const int nch = ceil_div(frame_off[f + 1] - frame_off[f], kChunk);
       int s = 0;
-      for (int cidx = threadIdx.x; cidx < nch; cidx += 32) s += W.chunk_count[f * W.cpf_cap + cidx];
-#pragma unroll
-      for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-      if (f < b) base += min(s, P.max_voxels);
-      else if (threadIdx.x == 0) sm_chunk_prefix = s;
+      for (int cidx = 0; cidx < nch; cidx++) s += W.chunk_count[f * W.cpf_cap + cidx];
+      part += min(s, P.max_voxels);
     }
-    if (threadIdx.x == 0) sm_frame_base = base;
+    for (int cidx = threadIdx.x; cidx < (int)blockIdx.x; cidx += blockDim.x) cp += W.chunk_count[b * W.cpf_cap + cidx];
+    int tot_part, tot_cp;
+    block_exclusive_scan(part, sm_scan, tot_part);
+    block_exclusive_scan(cp, sm_scan, tot_cp);
+    if (threadIdx.x == 0) {
+      sm_frame_base = tot_part;
+      sm_chunk_prefix = tot_cp;
+    }
   }
   __syncthreads();
   const int il = blockIdx.x * kChunk + threadIdx.x;

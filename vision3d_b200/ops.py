@@ -300,6 +300,26 @@ def sparse_to_dense(feat, indices, n_rows, capacity_rows, batch_size, shape, out
     return out
 
 
+def sparse_to_bev_nhwc(feat, indices, n_rows, capacity_rows, batch_size, shape, out=None, workspace=None):
+    """BEV map (B, C*D, H, W) in torch channels_last memory (= (B,H,W,C*D) storage), channel = c*D + d:
+    the tensor `dense().view(B, C*D, H, W)` of the reference, laid out the way cuDNN wants it."""
+    C = feat.shape[1]
+    dev = feat.device
+    if out is None:
+        out = torch.empty((batch_size, C * shape[0], shape[1], shape[2]), dtype=_F32, device=dev,
+                          memory_format=torch.channels_last)
+    assert out.is_contiguous(memory_format=torch.channels_last)
+    if workspace is None:
+        nbytes = _lib.load().v3d_sparse_to_dense_workspace_bytes(int(batch_size), i3(shape))
+        workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().v3d_sparse_to_dense_nhwc(feat.data_ptr(), indices.data_ptr(), n_rows.data_ptr(),
+                                                   int(capacity_rows), C, int(batch_size), i3(shape),
+                                                   out.data_ptr(), workspace.data_ptr(), workspace.numel(),
+                                                   _stream()), "v3d_sparse_to_dense_nhwc")
+    return out
+
+
 # =============================================================================================
 # a7-a10: point ops (pointnet2_utils names and argument order)
 # =============================================================================================

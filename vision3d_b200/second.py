@@ -194,8 +194,9 @@ class HeadB200(nn.Module):
     def forward(self, fmap):
         cfg = self.cfg
         B, _, ny, nx = fmap.shape
-        cls_map = self.conv_cls(fmap).view(B, cfg.NUM_CLASSES, cfg.NUM_YAW, ny, nx)
-        reg_map = self.conv_reg(fmap).view(B, cfg.NUM_CLASSES, cfg.BOX_DOF, -1, ny, nx).permute(0, 1, 3, 4, 5, 2)
+        # reshape (not view): the feature map may arrive in channels_last memory
+        cls_map = self.conv_cls(fmap).reshape(B, cfg.NUM_CLASSES, cfg.NUM_YAW, ny, nx)
+        reg_map = self.conv_reg(fmap).reshape(B, cfg.NUM_CLASSES, cfg.BOX_DOF, -1, ny, nx).permute(0, 1, 3, 4, 5, 2)
         return cls_map, reg_map
 
     def candidates(self, fmap, anchors):
@@ -441,8 +442,18 @@ class SecondEngine:
                              x, d["w"], self.nbr_conv[lv], self.n_rows[lv + 1], self.caps[lv + 1], d["scale"],
                              d["shift"], True, out=out))))
             x, li = out, li + 1
-        plan.append(("dense", 2, (lambda x=x: ops.sparse_to_dense(
-            x, self.indices[4], self.n_rows[4], self.caps[4], B, self.shapes[4], self.dense_out, self.dense_ws))))
+        if self.rpn_mode == "fused_nhwc":
+            # BEV map written directly in channels_last memory (what cuDNN's sm_100 kernels consume)
+            sh = self.shapes[4]
+            self.bev_nhwc = torch.empty((B, 64 * sh[0], sh[1], sh[2]), dtype=torch.float32, device=self.dev,
+                                        memory_format=torch.channels_last)
+            plan.append(("dense", 2, (lambda x=x: ops.sparse_to_bev_nhwc(
+                x, self.indices[4], self.n_rows[4], self.caps[4], B, self.shapes[4], self.bev_nhwc,
+                self.dense_ws))))
+        else:
+            plan.append(("dense", 2, (lambda x=x: ops.sparse_to_dense(
+                x, self.indices[4], self.n_rows[4], self.caps[4], B, self.shapes[4], self.dense_out,
+                self.dense_ws))))
         plan.append(("rpn(cudnn)", 0, self._rpn))
         plan.append(("head_topk_decode(torch)", 0, self._head))
         plan.append(("nms_rotated", 3, self._nms))
@@ -452,12 +463,13 @@ class SecondEngine:
 
     def _rpn(self):
         B = self.B
-        x = self.dense_out.view(B, 64 * self.shapes[4][0], self.shapes[4][1], self.shapes[4][2])
+        if self.rpn_mode == "fused_nhwc":
+            x = self.bev_nhwc
+        else:
+            x = self.dense_out.view(B, 64 * self.shapes[4][0], self.shapes[4][1], self.shapes[4][2])
         if self.rpn_mode == "module":
             self._fmap = self.model.rpn(x)
             return
-        if self.rpn_mode == "fused_nhwc":
-            x = x.contiguous(memory_format=torch.channels_last)
         for w, b, pad in self.rpn_folded:
             x = torch.cudnn_convolution_relu(x, w, b, [1, 1], pad, [1, 1], 1)
         self._fmap = x
