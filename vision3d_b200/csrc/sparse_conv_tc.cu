@@ -1,28 +1,32 @@
 // a5 + a6 on the 5th-generation tensor cores: output-stationary sparse convolution with tcgen05.mma
-// (kind::tf32, 3xTF32 split for fp32-grade accuracy), accumulators in TMEM, folded BN + ReLU epilogue.
+// (kind::tf32, 3xTF32 split for fp32-grade accuracy), accumulators AND the gathered A operand in TMEM,
+// folded BN + ReLU epilogue.
 //
-// One persistent CTA per SM, warp specialised:
+// One persistent CTA per SM, warp specialised (448 threads):
 //   warps 0-3  epilogue   : tcgen05.ld the 128 x COUT fp32 accumulator (lane = output row), apply
 //                           scale/shift/ReLU, store each output row once
 //   warp  4    MMA issuer : one elected thread; per pipeline slot issues 3*(CIN/8) tcgen05.mma
-//                           (A_hi*B_hi + A_lo*B_hi + A_hi*B_lo) M=128, N=COUT, K=8; tcgen05.commit
-//                           frees the slot / publishes the accumulator through mbarriers
-//   warp  5    weight TMA : one thread; cp.async.bulk (1-D TMA) of the pre-swizzled, pre-split W[kk]
-//                           image (hi+lo) into the slot, completion on the slot's mbarrier
-//   warps 6-13 gatherers  : two independent groups of 4 warps, pipeline slot q belongs to group q % 2.
-//                           A group stages the tile's rule rows (all KV offsets x 128 outputs), skips
-//                           offsets no row of the tile uses, gathers the neighbour feature rows with
-//                           128-bit loads issued up to kDepth slots AHEAD into registers (the load
-//                           latency overlaps the MMAs of earlier slots and the other group's work),
-//                           then splits every value into tf32 hi / lo parts and writes them into the
-//                           128B-swizzled K-major UMMA layout once the slot is free
+//                           (A_lo*B_hi + A_hi*B_lo + A_hi*B_hi) M=128, N=COUT, K=8 with A read from
+//                           TMEM and B from shared memory; tcgen05.commit frees the A stage, the B
+//                           stage and publishes the accumulator through mbarriers
+//   warp  5    weight TMA : finds the kernel offsets each tile uses and streams the pre-swizzled,
+//                           pre-split W[kk] images (hi+lo) with cp.async.bulk (1-D TMA) into a deep
+//                           shared-memory ring, running up to kBStages slots ahead of the MMAs
+//   warps 6-13 gatherers  : two independent groups of 4 warps, slot q belongs to group q % 2; thread =
+//                           output row. A thread gathers its neighbour's feature row with 128-bit
+//                           loads issued up to kDepth slots AHEAD into registers, splits every value
+//                           into tf32 hi / lo parts and tcgen05.st's them into the TMEM A stage.
+// Why A goes through TMEM: with both operands in shared memory a 3xTF32 N=64 tile is bound by the
+// 128 B/clk shared-memory port (each K=8 step re-reads 4 KB of A three times: measured 2900 clk per
+// slot against 830 clk of tensor math). TMEM-resident A leaves only the 2 KB B reads on that port.
 // Output rows are written exactly once (no atomics, deterministic). Arithmetic: every product is
 // exact in fp32 (11-bit x 11-bit mantissas); dropping only a_lo*b_lo bounds the relative error of a
 // product by ~2^-21, far inside the 1e-4 the contract allows.
 //
-// Shared-memory operand layout (both operands K-major, SWIZZLE_128B, fp32 elements): a "chunk" is
-// rows x 128 bytes (32 K-elements); 8-row groups are 1024 B apart (SBO); the 16-byte unit u of row r
-// lives at unit u ^ (r & 7). CIN = 64 uses two chunks, CIN = 16 uses half of one.
+// B operand layout (K-major, SWIZZLE_128B, fp32 elements): a "chunk" is COUT rows x 128 bytes
+// (32 K-elements); 8-row groups are 1024 B apart (SBO); the 16-byte unit u of row r lives at unit
+// u ^ (r & 7). CIN = 64 uses two chunks, CIN = 16 uses half of one.
+// TMEM columns: [0, 2*COUT) two accumulator buffers; then kAStages x (CIN hi | CIN lo) A stages.
 #include "common.cuh"
 
 namespace v3d {
@@ -97,30 +101,52 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+      "%15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+
+constexpr int pow2_cols(int c) { return c <= 32 ? 32 : (c <= 64 ? 64 : (c <= 128 ? 128 : (c <= 256 ? 256 : 512))); }
+
 template <int CIN, int COUT>
 struct TcCfg {
   static constexpr int kChunks = (CIN + 31) / 32;
   static constexpr int kKSteps = CIN / 8;
-  static constexpr int kUnitsPerRow = CIN / 4;                      // 16-byte units in a feature row
-  static constexpr int kAChunkBytes = kTileM * 128;                 // 16 KB
+  static constexpr int kUnitsPerRow = CIN / 4;                // float4 loads per gathered row
   static constexpr int kBChunkBytes = COUT * 128;
-  static constexpr int kAPartBytes = kChunks * kAChunkBytes;        // hi or lo
-  static constexpr int kBPartBytes = kChunks * kBChunkBytes;
-  static constexpr int kABytes = 2 * kAPartBytes;
-  static constexpr int kBBytes = 2 * kBPartBytes;                   // == one prepared W[kk] image
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (CIN >= 64) ? 2 : 3;
-  static constexpr int kItems = kTileM * kUnitsPerRow / (kGatherWarps * 32);  // float4 loads per thread and slot
-  static constexpr int kDepth = kItems >= 16 ? 1 : (kItems >= 8 ? 2 : 4);     // register sets (slots in flight)
-  static constexpr int kTmemCols = (2 * COUT <= 32) ? 32 : (2 * COUT <= 64 ? 64 : (2 * COUT <= 128 ? 128 : 256));
-  static constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * kStageBytes +
+  static constexpr int kBPartBytes = kChunks * kBChunkBytes;  // hi or lo
+  static constexpr int kBBytes = 2 * kBPartBytes;             // == one prepared W[kk] image
+  static constexpr int kBStagesFit = (160 * 1024) / kBBytes;
+  static constexpr int kBStages = kBStagesFit > 8 ? 8 : kBStagesFit;
+  static constexpr int kAccCols = 2 * COUT;
+  static constexpr int kAStageCols = 2 * CIN;                 // hi | lo
+  static constexpr int kAStagesFit = (512 - kAccCols) / kAStageCols;
+  static constexpr int kAStages = kAStagesFit > 4 ? 4 : kAStagesFit;
+  static constexpr int kTmemCols = pow2_cols(kAccCols + kAStages * kAStageCols);
+  static constexpr int kDepth = kUnitsPerRow >= 16 ? 1 : (kUnitsPerRow >= 8 ? 2 : 4);  // register sets in flight
+  static constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kBStages * kBBytes +
                                        sizeof(int) * kGatherGroups * kMaxKV * kTileM +
                                        1024 /*barriers + meta*/ + 2 * COUT * sizeof(float);
+  static_assert(kAStages >= 2 && kBStages >= 2, "pipeline needs two stages");
 };
 
 struct SlotMeta {
-  int kk;    // kernel offset of this slot, or -1 = all tiles done
   int last;  // 1 = last slot of its output tile
+  int end;   // 1 = all tiles done
 };
 
 template <int CIN, int COUT>
@@ -132,16 +158,16 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
   using C = TcCfg<CIN, COUT>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  unsigned char* stages = base;                                             // kStages x (A_hi A_lo B_hi B_lo)
-  int* idx_tile = reinterpret_cast<int*>(base + (size_t)C::kStages * C::kStageBytes);  // [group][KV][128]
+  unsigned char* bring = base;                                                        // kBStages x (B_hi B_lo)
+  int* idx_tile = reinterpret_cast<int*>(base + (size_t)C::kBStages * C::kBBytes);    // [group][KV][128]
   unsigned char* tail = reinterpret_cast<unsigned char*>(idx_tile + kGatherGroups * kMaxKV * kTileM);
-  uint64_t* full_a = reinterpret_cast<uint64_t*>(tail);          // [kStages]
-  uint64_t* full_b = full_a + 4;
-  uint64_t* empty = full_b + 4;
-  uint64_t* meta_full = empty + 4;
-  uint64_t* acc_full = meta_full + 4;   // [2]
-  uint64_t* acc_empty = acc_full + 2;   // [2]
-  SlotMeta* meta = reinterpret_cast<SlotMeta*>(acc_empty + 2);  // [kStages]
+  uint64_t* full_a = reinterpret_cast<uint64_t*>(tail);  // [4]
+  uint64_t* empty_a = full_a + 4;                        // [4]
+  uint64_t* full_b = empty_a + 4;                        // [8]
+  uint64_t* empty_b = full_b + 8;                        // [8]
+  uint64_t* acc_full = empty_b + 8;                      // [2]
+  uint64_t* acc_empty = acc_full + 2;                    // [2]
+  SlotMeta* meta = reinterpret_cast<SlotMeta*>(acc_empty + 2);  // [4]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(meta + 4);
   uint32_t* tile_mask = tmem_slot + 1;  // [kGatherGroups]
   float* s_scale = reinterpret_cast<float*>(tail + 1024);
@@ -152,11 +178,13 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
   const int n_tiles = (n_out + kTileM - 1) / kTileM;
 
   if (tid == 0) {
-    for (int s = 0; s < C::kStages; s++) {
+    for (int s = 0; s < C::kAStages; s++) {
       mbar_init(&full_a[s], kGatherWarps * 32);  // the one group that owns the slot
+      mbar_init(&empty_a[s], 1);
+    }
+    for (int s = 0; s < C::kBStages; s++) {
       mbar_init(&full_b[s], 1);
-      mbar_init(&empty[s], 1);
-      mbar_init(&meta_full[s], 1);
+      mbar_init(&empty_b[s], 1);
     }
     for (int a = 0; a < 2; a++) {
       mbar_init(&acc_full[a], 1);
@@ -228,16 +256,17 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(kTileM, COUT);
-      uint32_t slot = 0, ph = 0;
+      uint32_t q = 0;
       int it = 0;
       bool done = false;
       while (!done) {
         const int a = it & 1;
         bool first = true, tile_open = false;
         while (true) {
-          mbar_wait(&full_a[slot], ph);
-          const SlotMeta m = meta[slot];
-          if (m.kk < 0) {
+          const uint32_t as = q % C::kAStages, bs = q % C::kBStages;
+          mbar_wait(&full_a[as], (q / C::kAStages) & 1u);
+          const SlotMeta m = meta[as];
+          if (m.end) {
             done = true;
             break;
           }
@@ -245,58 +274,74 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
             mbar_wait(&acc_empty[a], ((it >> 1) & 1) ^ 1);
             tile_open = true;
           }
-          mbar_wait(&full_b[slot], ph);
+          mbar_wait(&full_b[bs], (q / C::kBStages) & 1u);
           tc_fence_after();
-          unsigned char* st = stages + (size_t)slot * C::kStageBytes;
-          const uint32_t a_hi = smem_u32(st), a_lo = a_hi + C::kAPartBytes;
-          const uint32_t b_hi = a_hi + C::kABytes, b_lo = b_hi + C::kBPartBytes;
+          const uint32_t b_hi = smem_u32(bring + (size_t)bs * C::kBBytes), b_lo = b_hi + C::kBPartBytes;
+          const uint32_t a_hi = tmem_base + (uint32_t)(C::kAccCols + as * C::kAStageCols), a_lo = a_hi + CIN;
           const uint32_t d = tmem_base + (uint32_t)(a * COUT);
 #pragma unroll
           for (int ks = 0; ks < C::kKSteps; ks++) {
-            const uint32_t ao = (uint32_t)(ks >> 2) * C::kAChunkBytes + (uint32_t)(ks & 3) * 32u;
             const uint32_t bo = (uint32_t)(ks >> 2) * C::kBChunkBytes + (uint32_t)(ks & 3) * 32u;
-            const uint64_t dah = make_desc(a_hi + ao), dal = make_desc(a_lo + ao);
             const uint64_t dbh = make_desc(b_hi + bo), dbl = make_desc(b_lo + bo);
-            umma_tf32(d, dal, dbh, idesc, first ? 0u : 1u);  // small terms first
+            umma_tf32_ts(d, a_lo + 8u * ks, dbh, idesc, first ? 0u : 1u);  // small terms first
             first = false;
-            umma_tf32(d, dah, dbl, idesc, 1u);
-            umma_tf32(d, dah, dbh, idesc, 1u);
+            umma_tf32_ts(d, a_hi + 8u * ks, dbl, idesc, 1u);
+            umma_tf32_ts(d, a_hi + 8u * ks, dbh, idesc, 1u);
           }
-          umma_commit(&empty[slot]);  // slot reusable once these MMAs have read it
+          umma_commit(&empty_a[as]);  // stages reusable once these MMAs have read them
+          umma_commit(&empty_b[bs]);
           const int last = m.last;
           if (last) umma_commit(&acc_full[a]);
-          if (++slot == C::kStages) {
-            slot = 0;
-            ph ^= 1;
-          }
+          q++;
           if (last) break;
         }
         it++;
       }
     }
   } else if (warp == kEpiWarps + 1) {
-    // =========================== weight loader (1-D TMA) ===========================
-    if (lane == 0) {
-      uint32_t slot = 0, ph = 0;
-      while (true) {
-        mbar_wait(&meta_full[slot], ph);
-        const int kk = meta[slot].kk;
-        if (kk < 0) break;
-        unsigned char* st = stages + (size_t)slot * C::kStageBytes;
-        mbar_arrive_expect_tx(&full_b[slot], (uint32_t)C::kBBytes);
-        bulk_g2s(st + C::kABytes, wprep + (size_t)kk * C::kBBytes, (uint32_t)C::kBBytes, &full_b[slot]);
-        if (++slot == C::kStages) {
-          slot = 0;
-          ph ^= 1;
+    // =========================== weight loader (1-D TMA), whole warp ===========================
+    uint32_t q = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      // which kernel offsets does this tile use? lanes cover rows lane + 32 j; 9 offsets per round trip
+      const int o0 = tile * kTileM + lane;
+      uint32_t mask = 0;
+      for (int k0 = 0; k0 < KV; k0 += 9) {
+        int v[9][4];
+#pragma unroll
+        for (int u = 0; u < 9; u++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const int o = o0 + 32 * j;
+            v[u][j] = (k0 + u < KV && o < n_out) ? __ldg(&nbr[(size_t)(k0 + u) * nbr_stride + o]) : -1;
+          }
+#pragma unroll
+        for (int u = 0; u < 9; u++) {
+          const bool any = (v[u][0] >= 0) | (v[u][1] >= 0) | (v[u][2] >= 0) | (v[u][3] >= 0);
+          if (__any_sync(0xffffffffu, any)) mask |= 1u << (k0 + u);
         }
       }
+      if (mask == 0) mask = 1u;  // must mirror the gatherers' rule
+      while (mask) {
+        const int kk = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const uint32_t bs = q % C::kBStages;
+        if (lane == 0) {
+          mbar_wait(&empty_b[bs], ((q / C::kBStages) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&full_b[bs], (uint32_t)C::kBBytes);
+          bulk_g2s(bring + (size_t)bs * C::kBBytes, wprep + (size_t)kk * C::kBBytes, (uint32_t)C::kBBytes,
+                   &full_b[bs]);
+        }
+        q++;
+      }
+      __syncwarp();
     }
   } else {
     // =========================== gatherers ===========================
     constexpr int NG = kGatherWarps * 32;
-    constexpr int UPR = C::kUnitsPerRow, ITEMS = C::kItems, DEPTH = C::kDepth;
+    constexpr int UPR = C::kUnitsPerRow, DEPTH = C::kDepth;
     const int gtid = tid - 32 * (kEpiWarps + 2);
     const int grp = gtid / NG, gt = gtid % NG;
+    const int my_row = 32 * (warp & 3) + lane;  // TMEM lane == tile row; a warp may only touch its lane quarter
     int* idx_g = idx_tile + grp * kMaxKV * kTileM;
     uint32_t* mask_g = tile_mask + grp;
 
@@ -320,9 +365,6 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
         // stage this tile's rule rows (group-private copy) and find the offsets it uses
         asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(NG) : "memory");  // loads that used idx_g are issued
         if (gt == 0) *mask_g = 0u;
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(NG) : "memory");
-        // all KV loads of this thread are independent: issue them back to back (no warp-level op in
-        // between -- a ballot per load would serialise 27 L2 round trips per tile)
         const int o = cur_tile * kTileM + gt;
         {
           const int* src = nbr + o;
@@ -334,7 +376,6 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
         }
         asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(NG) : "memory");
         {
-          // which offsets does the tile use at all? warp w inspects offsets w, w+4, ...
           const int w = gt >> 5;
           uint32_t mine = 0;
           for (int k2 = w; k2 < KV; k2 += kGatherWarps) {
@@ -350,22 +391,18 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
       }
     };
 
-    float4 v[DEPTH][ITEMS];
-    int it_kk[DEPTH], it_last[DEPTH];
+    float4 v[DEPTH][UPR];
+    int it_last[DEPTH];
     uint32_t it_q[DEPTH];
     bool it_ok[DEPTH];
     auto issue = [&](int d) {
-      it_ok[d] = next_item(it_kk[d], it_last[d], it_q[d]);
+      int kk;
+      it_ok[d] = next_item(kk, it_last[d], it_q[d]);
       if (!it_ok[d]) return;
-      const int* idx = idx_g + it_kk[d] * kTileM;
+      const int src = idx_g[kk * kTileM + my_row];
+      const float4* rowp = reinterpret_cast<const float4*>(feat + (size_t)(src >= 0 ? src : 0) * CIN);
 #pragma unroll
-      for (int i = 0; i < ITEMS; i++) {
-        const int u = i * NG + gt;
-        const int r = u / UPR, j = u % UPR;
-        const int src = idx[r];
-        v[d][i] = src >= 0 ? __ldg(reinterpret_cast<const float4*>(feat + (size_t)src * CIN) + j)
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      for (int i = 0; i < UPR; i++) v[d][i] = src >= 0 ? __ldg(rowp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
 #pragma unroll
     for (int d = 0; d < DEPTH; d++) it_ok[d] = false;
@@ -376,6 +413,7 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
       for (int e = 0; e < d; e++) prev_ok = prev_ok && it_ok[e];
       if (prev_ok) issue(d);
     }
+    const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
     bool running = true;
     while (running) {
 #pragma unroll
@@ -386,47 +424,46 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
           break;
         }
         const uint32_t q = it_q[d];
-        const uint32_t slot = q % C::kStages, use = q / C::kStages;
-        mbar_wait(&empty[slot], (use & 1u) ^ 1u);
+        const uint32_t as = q % C::kAStages;
+        mbar_wait(&empty_a[as], ((q / C::kAStages) & 1u) ^ 1u);
+        tc_fence_after();
         if (gt == 0) {
-          meta[slot].kk = it_kk[d];
-          meta[slot].last = it_last[d];
-          mbar_arrive(&meta_full[slot]);  // weight loader may start (release orders the meta writes)
+          meta[as].last = it_last[d];
+          meta[as].end = 0;
         }
-        unsigned char* st = stages + (size_t)slot * C::kStageBytes;
+        const uint32_t a_hi = tmem_base + lane_base + (uint32_t)(C::kAccCols + as * C::kAStageCols);
 #pragma unroll
-        for (int i = 0; i < ITEMS; i++) {
-          const int u = i * NG + gt;
-          const int r = u / UPR, j = u % UPR;
-          const uint32_t off = (uint32_t)(j >> 3) * C::kAChunkBytes + (uint32_t)(r >> 3) * 1024u +
-                               (uint32_t)(r & 7) * 128u + (uint32_t)(((j & 7) ^ (r & 7)) << 4);
-          float4 hi, lo;
-          hi.x = __uint_as_float(__float_as_uint(v[d][i].x) & 0xFFFFE000u);
-          hi.y = __uint_as_float(__float_as_uint(v[d][i].y) & 0xFFFFE000u);
-          hi.z = __uint_as_float(__float_as_uint(v[d][i].z) & 0xFFFFE000u);
-          hi.w = __uint_as_float(__float_as_uint(v[d][i].w) & 0xFFFFE000u);
-          lo.x = v[d][i].x - hi.x;
-          lo.y = v[d][i].y - hi.y;
-          lo.z = v[d][i].z - hi.z;
-          lo.w = v[d][i].w - hi.w;
-          *reinterpret_cast<float4*>(st + off) = hi;
-          *reinterpret_cast<float4*>(st + C::kAPartBytes + off) = lo;
+        for (int c16 = 0; c16 < CIN / 16; c16++) {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const float4 x = v[d][4 * c16 + u];
+            const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              const uint32_t h = __float_as_uint(xs[e]) & 0xFFFFE000u;
+              hi[4 * u + e] = h;
+              lo[4 * u + e] = __float_as_uint(xs[e] - __uint_as_float(h));
+            }
+          }
+          tmem_st16(a_hi + 16u * c16, hi);
+          tmem_st16(a_hi + (uint32_t)CIN + 16u * c16, lo);
         }
-        fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-        mbar_arrive(&full_a[slot]);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        mbar_arrive(&full_a[as]);  // release also orders the meta write of gt == 0
         issue(d);  // refill this register set: loads fly while the other sets / the other group are processed
       }
     }
     // termination slot: sequence number = total slot count, posted by the group that owns it
     if ((int)(q_next % kGatherGroups) == grp) {
-      const uint32_t slot = q_next % C::kStages, use = q_next / C::kStages;
-      mbar_wait(&empty[slot], (use & 1u) ^ 1u);
+      const uint32_t as = q_next % C::kAStages;
+      mbar_wait(&empty_a[as], ((q_next / C::kAStages) & 1u) ^ 1u);
       if (gt == 0) {
-        meta[slot].kk = -1;
-        meta[slot].last = 1;
-        mbar_arrive(&meta_full[slot]);
+        meta[as].last = 1;
+        meta[as].end = 1;
       }
-      mbar_arrive(&full_a[slot]);
+      mbar_arrive(&full_a[as]);
     }
   }
 

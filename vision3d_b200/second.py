@@ -205,7 +205,7 @@ class HeadB200(nn.Module):
         cfg = self.cfg
         cls_map, reg_map = self(fmap)
         B, n_cls = cls_map.shape[:2]
-        scores, a_idx = cls_map.sigmoid().view(B, n_cls, -1).topk(cfg.TOPK, -1)
+        scores, a_idx = cls_map.sigmoid().reshape(B, n_cls, -1).topk(cfg.TOPK, -1)
         g = a_idx[..., None].expand(-1, -1, -1, cfg.BOX_DOF)
         deltas = reg_map.reshape(B, n_cls, -1, cfg.BOX_DOF).gather(2, g)
         anc = anchors.view(1, n_cls, -1, cfg.BOX_DOF).expand(B, -1, -1, -1).gather(2, g)
