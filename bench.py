@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=16, help="frames per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--rpn", default="fused", choices=["module", "fused", "fused_nhwc"])
+    ap.add_argument("--rpn", default="fused_nhwc", choices=["module", "fused", "fused_nhwc"])
     ap.add_argument("--simt", action="store_true", help="exact-fp32 SIMT sparse conv instead of tcgen05 3xTF32")
     return ap.parse_args()
 

@@ -120,6 +120,12 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
       : "memory");
 }
 
+__device__ __forceinline__ void ldg256(const float* p, float (&v)[8]) {
+  asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+
 constexpr int pow2_cols(int c) { return c <= 32 ? 32 : (c <= 64 ? 64 : (c <= 128 ? 128 : (c <= 256 ? 256 : 512))); }
 
 template <int CIN, int COUT>
@@ -137,7 +143,7 @@ struct TcCfg {
   static constexpr int kAStagesFit = (512 - kAccCols) / kAStageCols;
   static constexpr int kAStages = kAStagesFit > 4 ? 4 : kAStagesFit;
   static constexpr int kTmemCols = pow2_cols(kAccCols + kAStages * kAStageCols);
-  static constexpr int kDepth = kUnitsPerRow >= 16 ? 1 : (kUnitsPerRow >= 8 ? 2 : 4);  // register sets in flight
+  static constexpr int kDepth = kUnitsPerRow >= 16 ? 1 : (kUnitsPerRow >= 8 ? 2 : 4);  // register sets in flight (64 floats each at CIN = 64)
   static constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kBStages * kBBytes +
                                        sizeof(int) * kGatherGroups * kMaxKV * kTileM +
                                        1024 /*barriers + meta*/ + 2 * COUT * sizeof(float);
@@ -391,7 +397,12 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
       }
     };
 
-    float4 v[DEPTH][UPR];
+    // Register image of one gathered row: CIN/16 pairs of 32-byte chunks. Lanes 2i and 2i+1 cooperate:
+    // a 256-bit load instruction reads 64 contiguous bytes of ONE row with the two lanes (first the even
+    // lane's row, then the odd lane's), so a warp-wide LDG touches 16 lines instead of 32 (the kernel is
+    // bound by L1 wavefronts otherwise); the halves are swapped back with shfl.xor before the TMEM store.
+    constexpr int NJ = CIN / 16;
+    float v[DEPTH][NJ][2][8];  // [j][0] = loaded from the even lane's row, [j][1] = from the odd lane's row
     int it_last[DEPTH];
     uint32_t it_q[DEPTH];
     bool it_ok[DEPTH];
@@ -400,9 +411,22 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
       it_ok[d] = next_item(kk, it_last[d], it_q[d]);
       if (!it_ok[d]) return;
       const int src = idx_g[kk * kTileM + my_row];
-      const float4* rowp = reinterpret_cast<const float4*>(feat + (size_t)(src >= 0 ? src : 0) * CIN);
+      const int src_e = __shfl_sync(0xffffffffu, src, lane & ~1);
+      const int src_o = __shfl_sync(0xffffffffu, src, lane | 1);
+      const int half = lane & 1;  // which 32-byte half of every 64-byte segment this lane fetches
 #pragma unroll
-      for (int i = 0; i < UPR; i++) v[d][i] = src >= 0 ? __ldg(rowp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < NJ; j++) {
+#pragma unroll
+        for (int w = 0; w < 2; w++) {
+          const int sr = w ? src_o : src_e;
+          if (sr >= 0) {
+            ldg256(feat + (size_t)sr * CIN + 16 * j + 8 * half, v[d][j][w]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; e++) v[d][j][w][e] = 0.f;
+          }
+        }
+      }
     };
 #pragma unroll
     for (int d = 0; d < DEPTH; d++) it_ok[d] = false;
@@ -433,21 +457,28 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
         }
         const uint32_t a_hi = tmem_base + lane_base + (uint32_t)(C::kAccCols + as * C::kAStageCols);
 #pragma unroll
-        for (int c16 = 0; c16 < CIN / 16; c16++) {
+        for (int j = 0; j < NJ; j++) {
+          // swap halves inside the lane pair: the even lane gives away what it fetched of the odd lane's
+          // row ([j][1]) and receives the upper half of its own row; the odd lane the other way round
+          float own[16];
+          const int half = lane & 1;
+#pragma unroll
+          for (int e = 0; e < 8; e++) {
+            const float give = half ? v[d][j][0][e] : v[d][j][1][e];
+            const float got = __shfl_xor_sync(0xffffffffu, give, 1);
+            const float keep = half ? v[d][j][1][e] : v[d][j][0][e];
+            own[e] = half ? got : keep;       // columns 16j + 0..7  of my row
+            own[8 + e] = half ? keep : got;   // columns 16j + 8..15 of my row
+          }
           uint32_t hi[16], lo[16];
 #pragma unroll
-          for (int u = 0; u < 4; u++) {
-            const float4 x = v[d][4 * c16 + u];
-            const float xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-              const uint32_t h = __float_as_uint(xs[e]) & 0xFFFFE000u;
-              hi[4 * u + e] = h;
-              lo[4 * u + e] = __float_as_uint(xs[e] - __uint_as_float(h));
-            }
+          for (int e = 0; e < 16; e++) {
+            const uint32_t h = __float_as_uint(own[e]) & 0xFFFFE000u;
+            hi[e] = h;
+            lo[e] = __float_as_uint(own[e] - __uint_as_float(h));
           }
-          tmem_st16(a_hi + 16u * c16, hi);
-          tmem_st16(a_hi + (uint32_t)CIN + 16u * c16, lo);
+          tmem_st16(a_hi + 16u * j, hi);
+          tmem_st16(a_hi + (uint32_t)CIN + 16u * j, lo);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
