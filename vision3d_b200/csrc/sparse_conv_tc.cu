@@ -111,6 +111,16 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
       : "memory");
 }
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
@@ -260,19 +270,25 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
     }
   } else if (warp == kEpiWarps) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    // The WHOLE warp walks the slot sequence with warp-uniform control flow and only the tcgen05
+    // instructions are predicated on one elected lane: operands then live in uniform registers. (With a
+    // single divergent thread every UTCHMMA needed ELECT + R2UR moves: ~380 SASS instructions and ~2500
+    // clk of issue time per slot, three times the 768 clk the tensor pipe needs.)
+    {
       constexpr uint32_t idesc = make_idesc(kTileM, COUT);
+      const uint32_t b_ring = smem_u32(bring);
       uint32_t q = 0;
       int it = 0;
       bool done = false;
       while (!done) {
         const int a = it & 1;
-        bool first = true, tile_open = false;
+        uint32_t accum = 0u;
+        bool tile_open = false;
         while (true) {
           const uint32_t as = q % C::kAStages, bs = q % C::kBStages;
           mbar_wait(&full_a[as], (q / C::kAStages) & 1u);
-          const SlotMeta m = meta[as];
-          if (m.end) {
+          const int m_last = meta[as].last, m_end = meta[as].end;
+          if (m_end) {
             done = true;
             break;
           }
@@ -282,24 +298,28 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
           }
           mbar_wait(&full_b[bs], (q / C::kBStages) & 1u);
           tc_fence_after();
-          const uint32_t b_hi = smem_u32(bring + (size_t)bs * C::kBBytes), b_lo = b_hi + C::kBPartBytes;
+          const uint32_t b_hi = b_ring + bs * (uint32_t)C::kBBytes;
+          const uint64_t dbh0 = make_desc(b_hi), dbl0 = make_desc(b_hi + (uint32_t)C::kBPartBytes);
           const uint32_t a_hi = tmem_base + (uint32_t)(C::kAccCols + as * C::kAStageCols), a_lo = a_hi + CIN;
           const uint32_t d = tmem_base + (uint32_t)(a * COUT);
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < C::kKSteps; ks++) {
-            const uint32_t bo = (uint32_t)(ks >> 2) * C::kBChunkBytes + (uint32_t)(ks & 3) * 32u;
-            const uint64_t dbh = make_desc(b_hi + bo), dbl = make_desc(b_lo + bo);
-            umma_tf32_ts(d, a_lo + 8u * ks, dbh, idesc, first ? 0u : 1u);  // small terms first
-            first = false;
-            umma_tf32_ts(d, a_hi + 8u * ks, dbl, idesc, 1u);
-            umma_tf32_ts(d, a_hi + 8u * ks, dbh, idesc, 1u);
+            for (int ks = 0; ks < C::kKSteps; ks++) {
+              // descriptor start address advances in 16-byte units (low 14 bits of the descriptor)
+              const uint64_t bo = (uint64_t)(((ks >> 2) * C::kBChunkBytes + (ks & 3) * 32) >> 4);
+              umma_tf32_ts(d, a_lo + 8u * ks, dbh0 + bo, idesc, accum);  // small terms first
+              umma_tf32_ts(d, a_hi + 8u * ks, dbl0 + bo, idesc, 1u);
+              umma_tf32_ts(d, a_hi + 8u * ks, dbh0 + bo, idesc, 1u);
+              accum = 1u;
+            }
+            umma_commit(&empty_a[as]);  // stages reusable once these MMAs have read them
+            umma_commit(&empty_b[bs]);
+            if (m_last) umma_commit(&acc_full[a]);
           }
-          umma_commit(&empty_a[as]);  // stages reusable once these MMAs have read them
-          umma_commit(&empty_b[bs]);
-          const int last = m.last;
-          if (last) umma_commit(&acc_full[a]);
+          accum = 1u;
+          __syncwarp();
           q++;
-          if (last) break;
+          if (m_last) break;
         }
         it++;
       }
