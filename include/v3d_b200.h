@@ -147,6 +147,22 @@ V3D_API int v3d_rulebook_conv(const void* in_table, const int* indices, const in
                               int* out_indices, int* n_out, int out_capacity, int* nbr, int nbr_stride,
                               void* workspace, size_t workspace_bytes, v3d_stream_t stream);
 
+/* Rank-indexed variants: a level PRODUCED by v3d_rulebook_conv has its rows in ascending flat order, and
+ * that call's workspace (bitmap + two-level popcount prefix) is a complete site index of the level
+ * (row = number of active cells before the cell). These variants use it instead of a hash table:
+ * `level_index` / `in_level_index` = the workspace pointer of the v3d_rulebook_conv call that produced the
+ * level, `index_capacity` = the out_capacity passed to that call, shape = that level's shape. */
+V3D_API int v3d_rulebook_subm_ranked(const void* level_index, int B, int index_capacity, const int* indices,
+                                     const int* n_rows, int capacity_rows, const int* shape_host,
+                                     const int* ksize_host, const int* dilation_host, int* nbr, int nbr_stride,
+                                     v3d_stream_t stream);
+V3D_API int v3d_rulebook_conv_ranked(const void* in_level_index, int in_index_capacity, const int* indices,
+                                     const int* n_rows, int capacity_rows, int B, const int* shape_host,
+                                     const int* ksize_host, const int* stride_host, const int* pad_host,
+                                     const int* dilation_host, int* out_indices, int* n_out, int out_capacity,
+                                     int* nbr, int nbr_stride, void* workspace, size_t workspace_bytes,
+                                     v3d_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * a5 + a6  sparse convolution forward with the eval-mode BatchNorm1d + ReLU that
  * spconv.SparseSequential applies next folded into the epilogue

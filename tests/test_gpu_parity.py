@@ -444,3 +444,29 @@ def test_prepared_weights_fall_back_to_exact_path_for_cin4(cuda):
     from vision3d_b200 import ops
     pw = ops.PreparedWeights(torch.randn(27, 4, 16, device=cuda))
     assert pw.buf is None  # Cin = 4 stays on the exact-fp32 SIMT kernel
+
+
+def test_rank_indexed_rulebooks_match_hash_and_oracle(cuda):
+    """Levels produced by a strided conv are indexed by that conv's bitmap/prefix workspace: SubM and the next
+    strided conv built from it must equal the oracle (and therefore the hash-table path)."""
+    from vision3d_b200 import ops
+    shape, B = [11, 120, 96], 3
+    idx0 = synth.make_clustered_sites(21, 5000, shape, B)
+    ind, n_rows, table, cap = _site_setup(cuda, idx0, shape)
+    # level 0 -> 1 (hash-indexed input)
+    o1, nbr1_want, shape1 = oracle.rulebook_conv(idx0, shape, 3, 2, 1)
+    cap1 = len(o1) + 100
+    ws1 = ops.ConvRulebookWorkspace(B, shape1, cap1, 27, cuda)
+    out1, n1, nbr1, sh1 = ops.rulebook_conv(table, ind, n_rows, B, shape, 3, 2, 1, 1, cap1, workspace=ws1)
+    assert sh1 == shape1 and int(n1.item()) == len(o1)
+    assert np.array_equal(out1[:len(o1)].cpu().numpy(), o1)
+    # SubM on level 1 through the rank index
+    nbr_s = ops.rulebook_subm(ws1, out1, n1, shape1, 3, 1, capacity=cap1)
+    assert np.array_equal(nbr_s[:, :len(o1)].cpu().numpy(), oracle.rulebook_subm(o1, shape1, 3))
+    # level 1 -> 2 with the rank index as input index
+    o2, nbr2_want, shape2 = oracle.rulebook_conv(o1, shape1, 3, 2, [0, 1, 1])
+    cap2 = len(o2) + 50
+    out2, n2, nbr2, sh2 = ops.rulebook_conv(ws1, out1, n1, B, shape1, 3, 2, [0, 1, 1], 1, cap2)
+    assert sh2 == shape2 and int(n2.item()) == len(o2)
+    assert np.array_equal(out2[:len(o2)].cpu().numpy(), o2)
+    assert np.array_equal(nbr2[:, :len(o2)].cpu().numpy(), nbr2_want)

@@ -96,6 +96,26 @@ __global__ void __launch_bounds__(256) dense_nhwc_kernel(const float* __restrict
   }
 }
 
+// D == 2 (SECOND's final level): one thread owns two channels of one pixel and writes (c,d0)(c,d1)(c+1,d0)(c+1,d1)
+// as one 16-byte store -> a warp streams 512 contiguous bytes.
+__global__ void __launch_bounds__(256) dense_nhwc_d2_kernel(const float* __restrict__ feat,
+                                                            const int* __restrict__ cellmap, int C, int HW,
+                                                            int pixels_per_block, float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int half_c = C >> 1;
+  const int c2 = threadIdx.x % half_c;
+  const int pl = threadIdx.x / half_c;
+  const int per_iter = blockDim.x / half_c;
+  const int p_end = min(HW, (int)(blockIdx.x + 1) * pixels_per_block);
+  for (int p = blockIdx.x * pixels_per_block + pl; p < p_end; p += per_iter) {
+    const int r0 = __ldg(&cellmap[((size_t)b * 2 + 0) * HW + p]);
+    const int r1 = __ldg(&cellmap[((size_t)b * 2 + 1) * HW + p]);
+    const float2 f0 = r0 >= 0 ? __ldg(reinterpret_cast<const float2*>(feat + (size_t)r0 * C) + c2) : make_float2(0.f, 0.f);
+    const float2 f1 = r1 >= 0 ? __ldg(reinterpret_cast<const float2*>(feat + (size_t)r1 * C) + c2) : make_float2(0.f, 0.f);
+    reinterpret_cast<float4*>(out + ((size_t)b * HW + p) * C * 2)[c2] = make_float4(f0.x, f1.x, f0.y, f1.y);
+  }
+}
+
 }  // namespace
 }  // namespace v3d
 
@@ -120,6 +140,10 @@ extern "C" int v3d_sparse_to_dense_nhwc(const float* feat, const int* indices, c
                                           shape_host[0], shape_host[1], shape_host[2], B, cellmap);
   const int ppb = 16 * (256 / C);  // pixels per block
   dim3 grid((unsigned)ceil_div((int)HW, ppb), B);
+  if (D == 2 && (C % 2) == 0 && (256 % (C / 2)) == 0) {
+    dense_nhwc_d2_kernel<<<grid, 256, 0, st>>>(feat, cellmap, C, (int)HW, ppb, out);
+    return check_launch();
+  }
   switch (D) {
 #define V3D_NHWC_CASE(DD) \
   case DD:                \

@@ -225,92 +225,127 @@ __global__ void __launch_bounds__(kIouThreads) box_iou_kernel(const float* __res
 }
 
 // -------------------------------------------------------------------------------------------
-// a12: NMS, three launches.
+// a12: NMS, three launches, nothing leaves the device.
 // -------------------------------------------------------------------------------------------
 constexpr int kTile = 64;
 
-// (1) counting rank: position of box i in descending-score order, ties -> lower index first.
-//     Also writes the per-box invariants at the sorted position.
+// (1) counting rank: position of box i in descending-score order, ties -> lower index first; also writes
+//     the per-box invariants at the sorted position. One warp per box, lanes stride over the N scores.
+__device__ __forceinline__ float rank_key(float s) { return s != s ? __int_as_float(0x7f800000) : s; }  // NaN -> +inf
+
 __global__ void __launch_bounds__(256) nms_rank_kernel(const float* __restrict__ dets,
                                                        const float* __restrict__ scores, int N,
-                                                       int* __restrict__ order,
-                                                       BoxPre* __restrict__ pre) {
-  __shared__ float tile[1024];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  float si = 0.f;
-  if (i < N) {
-    si = scores[i];
-    if (si != si) si = __int_as_float(0x7f800000);  // NaN ranks as +inf
+                                                       int* __restrict__ order, BoxPre* __restrict__ pre) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= N) return;  // warp-uniform
+  const float si = rank_key(__ldg(&scores[i]));
+  int cnt = 0;
+  for (int j = lane; j < N; j += 32) {
+    const float sj = rank_key(__ldg(&scores[j]));
+    cnt += (sj > si) || (sj == si && j < i);
   }
-  int rank = 0;
-  for (int j0 = 0; j0 < N; j0 += 1024) {
-    __syncthreads();
-    for (int t = threadIdx.x; t < 1024; t += blockDim.x) {
-      float s = -__int_as_float(0x7f800000);
-      if (j0 + t < N) {
-        s = scores[j0 + t];
-        if (s != s) s = __int_as_float(0x7f800000);
-      }
-      tile[t] = s;
-    }
-    __syncthreads();
-    if (i < N) {
-      const int lim = min(1024, N - j0);
-      for (int t = 0; t < lim; t++) {
-        float sj = tile[t];
-        rank += (sj > si) || (sj == si && (j0 + t) < i);
-      }
-    }
-  }
-  if (i < N) {
-    order[rank] = i;
-    pre[rank] = make_pre(dets + (size_t)i * 5);
+#pragma unroll
+  for (int d = 16; d; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+  if (lane == 0) {
+    order[cnt] = i;
+    pre[cnt] = make_pre(dets + (size_t)i * 5);
   }
 }
 
-// (2) upper-triangular mask tiles. Block = 512 threads = 16 warps; warp w owns rows w*4..w*4+3 of
-//     the 64-row tile, lanes cover columns lane and lane+32; __ballot_sync assembles the words.
-constexpr int kMaskThreads = 512;
-constexpr int kMaskRowsPerWarp = kTile / (kMaskThreads / 32);
-__global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(const BoxPre* __restrict__ pre, int N, float thr,
-                                                       int col_blocks,
-                                                       unsigned long long* __restrict__ mask) {
+// (2) upper-triangular 64x64 mask tiles, ONE THREAD PER PAIR: block = (64 columns, 16 rows), 4 blocks per
+//     tile; a warp is half a row, __ballot_sync gives a 32-bit half of the row's mask word.
+constexpr int kMaskRows = 16;
+__global__ void __launch_bounds__(kTile * kMaskRows) nms_mask_kernel(const BoxPre* __restrict__ pre, int N,
+                                                                     float thr, int col_blocks,
+                                                                     unsigned int* __restrict__ mask32) {
   const int rb = blockIdx.y, cb = blockIdx.x;
   if (cb < rb) return;  // lower triangle is never read by the scan
-  __shared__ BoxPre rbox[kTile];
+  __shared__ BoxPre rbox[kMaskRows];
   __shared__ BoxPre cbox[kTile];
-  const int tid = threadIdx.x;
-  if (tid < kTile) {
-    if (rb * kTile + tid < N) rbox[tid] = pre[rb * kTile + tid];
-  } else if (tid < 2 * kTile) {
-    int t = tid - kTile;
-    if (cb * kTile + t < N) cbox[t] = pre[cb * kTile + t];
+  const int c = threadIdx.x, rl = threadIdx.y;
+  const int r = blockIdx.z * kMaskRows + rl;  // row inside the tile
+  const int gi = rb * kTile + r, gj = cb * kTile + c;
+  if (rl == 0 && gj < N) cbox[c] = pre[gj];
+  if (rl == 1 && c < kMaskRows) {
+    const int g = rb * kTile + blockIdx.z * kMaskRows + c;
+    if (g < N) rbox[c] = pre[g];
   }
   __syncthreads();
-  const int lane = tid & 31, warp = tid >> 5;
-  const int ncol = min(kTile, N - cb * kTile);
-#pragma unroll 1
-  for (int rr = 0; rr < kMaskRowsPerWarp; rr++) {
-    const int r = warp * kMaskRowsPerWarp + rr;
-    const int gi = rb * kTile + r;
-    if (gi >= N) break;  // warp-uniform
-    const BoxPre a = rbox[r];
-    unsigned int w[2];
-#pragma unroll
-    for (int half = 0; half < 2; half++) {
-      const int c = lane + 32 * half;
-      bool hit = false;
-      if (c < ncol && (rb != cb || c > r)) hit = iou_pair(a, cbox[c]) > thr;  // nms_rotated_cuda.cu:62-63
-      w[half] = __ballot_sync(0xffffffffu, hit);
-    }
-    if (lane == 0)
-      mask[(size_t)gi * col_blocks + cb] = ((unsigned long long)w[1] << 32) | (unsigned long long)w[0];
-  }
+  bool hit = false;
+  if (gi < N && gj < N && (rb != cb || c > r)) hit = iou_pair(rbox[rl], cbox[c]) > thr;  // nms_rotated_cuda.cu:62-63
+  const unsigned int w = __ballot_sync(0xffffffffu, hit);
+  if ((c & 31) == 0 && gi < N) mask32[((size_t)gi * col_blocks + cb) * 2 + (c >> 5)] = w;  // little endian halves
 }
 
-// (3) greedy scan (nms_rotated_cuda.cu:115-128) on the device: one block, one thread per mask word.
-//     Per 64-row chunk: thread 0 resolves the chunk against its diagonal word (64 dependent steps
-//     on registers/smem), then every thread ORs the kept rows' words into its removed-word.
+// (3a) greedy scan (nms_rotated_cuda.cu:115-128), N <= 8192: the 64 mask rows of chunk b+1 are prefetched
+//      into shared memory with cp.async while chunk b is resolved; the 64-step dependent chain runs on
+//      registers of one thread; kept rows are OR-ed into the removed-words from shared memory.
+constexpr int kScanThreads = 256;
+__global__ void __launch_bounds__(kScanThreads) nms_scan_smem_kernel(const unsigned long long* __restrict__ mask,
+                                                                     const int* __restrict__ order, int N,
+                                                                     int cb, long long* __restrict__ keep,
+                                                                     int* __restrict__ num_keep) {
+  extern __shared__ __align__(16) unsigned long long sm[];
+  unsigned long long* remv = sm;                       // [cb]
+  unsigned long long* buf0 = sm + ((cb + 1) & ~1);     // [64*cb] x 2, 16-byte aligned
+  unsigned long long* buf1 = buf0 + (size_t)kTile * cb;
+  __shared__ unsigned long long kept_bits;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int j = tid; j < cb; j += kScanThreads) remv[j] = 0ull;
+
+  auto prefetch = [&](int b, unsigned long long* dst) {
+    const int rows = min(kTile, N - b * kTile);
+    const size_t words = (size_t)rows * cb;            // contiguous in the mask array
+    const unsigned long long* src = mask + (size_t)b * kTile * cb;
+    for (size_t e = (size_t)tid * 2; e + 1 < words + 1; e += (size_t)kScanThreads * 2) {
+      if (e + 1 < words) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst + e)),
+                     "l"(src + e));
+      } else if (e < words) {
+        dst[e] = src[e];
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  prefetch(0, buf0);
+  int base = 0;
+  for (int b = 0; b < cb; b++) {
+    unsigned long long* cur = (b & 1) ? buf1 : buf0;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();  // chunk b rows visible; previous OR phase done
+    if (b + 1 < cb) prefetch(b + 1, (b & 1) ? buf0 : buf1);
+    const int rows = min(kTile, N - b * kTile);
+    if (tid == 0) {
+      unsigned long long removed = remv[b], kept = 0ull;
+#pragma unroll
+      for (int i = 0; i < kTile; i++) {
+        const unsigned long long d = i < rows ? cur[(size_t)i * cb + b] : 0ull;  // loads do not depend on the chain
+        const bool alive = i < rows && !((removed >> i) & 1ull);
+        kept |= alive ? (1ull << i) : 0ull;
+        removed |= alive ? d : 0ull;
+      }
+      kept_bits = kept;
+    }
+    __syncthreads();
+    const unsigned long long kept = kept_bits;
+    if (tid < rows && ((kept >> tid) & 1ull))
+      keep[base + __popcll(kept & ((1ull << tid) - 1ull))] = (long long)order[b * kTile + tid];
+    base += __popcll(kept);
+    for (int i = warp; i < rows; i += kScanThreads / 32) {
+      if (!((kept >> i) & 1ull)) continue;
+      const unsigned long long* row = cur + (size_t)i * cb;
+      for (int j = b + 1 + lane; j < cb; j += 32) {
+        const unsigned long long m = row[j];
+        if (m) atomicOr(&remv[j], m);
+      }
+    }
+  }
+  if (tid == 0) *num_keep = base;
+}
+
+// (3b) greedy scan for large N: one block, per 64-row chunk thread 0 resolves the chunk against its diagonal
+//      word, then one warp per kept row ORs the row's later words (all loads of the chunk in flight at once).
 __global__ void __launch_bounds__(1024) nms_scan_kernel(const unsigned long long* __restrict__ mask,
                                                         const int* __restrict__ order, int N,
                                                         int col_blocks, long long* __restrict__ keep,
@@ -327,7 +362,6 @@ __global__ void __launch_bounds__(1024) nms_scan_kernel(const unsigned long long
   for (int b = 0; b < col_blocks; b++) {
     const int rows = min(kTile, N - b * kTile);
     const int cur = b & 1;
-    // prefetch next chunk's diagonal words while this chunk is resolved
     if (tid >= 64 && tid < 64 + kTile && b + 1 < col_blocks) {
       int r = (b + 1) * kTile + (tid - 64);
       if (r < N) diag[cur ^ 1][tid - 64] = mask[(size_t)r * col_blocks + (b + 1)];
@@ -345,14 +379,10 @@ __global__ void __launch_bounds__(1024) nms_scan_kernel(const unsigned long long
     __syncthreads();
     const unsigned long long kept = kept_bits;
     const int base = kept_base;
-    // emit kept indices in order
     if (tid < rows && ((kept >> tid) & 1ull)) {
       int pos = base + __popcll(kept & ((1ull << tid) - 1ull));
       keep[pos] = (long long)order[b * kTile + tid];
     }
-    // suppress: OR the rows of kept boxes into the later words. One warp per kept row, lanes along
-    // the row's contiguous words: every load of the chunk is in flight at once (one global round
-    // trip per chunk instead of one per kept row), merged with shared-memory atomics.
     {
       const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
       for (int i = warp; i < rows; i += nwarps) {
@@ -415,7 +445,7 @@ extern "C" int v3d_nms_rotated(const float* dets, const float* scores, int N, fl
     return V3D_OK;
   }
   if (!dets || !scores || !keep || !workspace) return V3D_ERR_INVALID_ARGUMENT;
-  if (N > 65536) return V3D_ERR_INVALID_ARGUMENT;  // one scan thread per mask word, <=1024 words
+  if (N > 65536) return V3D_ERR_INVALID_ARGUMENT;  // mask words per row <= 1024
   NmsLayout l = nms_layout(N);
   if (workspace_bytes < l.total) return V3D_ERR_WORKSPACE_TOO_SMALL;
   char* ws = static_cast<char*>(workspace);
@@ -424,10 +454,21 @@ extern "C" int v3d_nms_rotated(const float* dets, const float* scores, int N, fl
   unsigned long long* mask = reinterpret_cast<unsigned long long*>(ws + l.mask_off);
   const int cb = ceil_div(N, kTile);
 
-  nms_rank_kernel<<<ceil_div(N, 256), 256, 0, st>>>(dets, scores, N, order, pre);
-  nms_mask_kernel<<<dim3(cb, cb), kMaskThreads, 0, st>>>(pre, N, iou_threshold, cb, mask);
-  const int scan_threads = 1024;  // 32 warps: two kept rows per warp in the suppress phase
-  nms_scan_kernel<<<1, scan_threads, sizeof(unsigned long long) * cb, st>>>(
-      mask, order, N, cb, reinterpret_cast<long long*>(keep), num_keep);
+  nms_rank_kernel<<<ceil_div(N, 8), 256, 0, st>>>(dets, scores, N, order, pre);
+  nms_mask_kernel<<<dim3(cb, cb, kTile / kMaskRows), dim3(kTile, kMaskRows), 0, st>>>(
+      pre, N, iou_threshold, cb, reinterpret_cast<unsigned int*>(mask));
+  const size_t smem_fast = sizeof(unsigned long long) * (((size_t)cb + 1) / 2 * 2 + 2 * (size_t)kTile * cb);
+  if (smem_fast <= 200 * 1024) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      V3D_CUDA_TRY(cudaFuncSetAttribute(nms_scan_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_set = true;
+    }
+    nms_scan_smem_kernel<<<1, kScanThreads, smem_fast, st>>>(mask, order, N, cb, reinterpret_cast<long long*>(keep),
+                                                            num_keep);
+  } else {
+    nms_scan_kernel<<<1, 1024, sizeof(unsigned long long) * cb, st>>>(mask, order, N, cb,
+                                                                     reinterpret_cast<long long*>(keep), num_keep);
+  }
   return check_launch();
 }

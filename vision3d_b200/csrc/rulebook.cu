@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(256) rule_lookup_kernel(SiteTable T, const int
 }
 
 // ---- strided conv: discover output sites --------------------------------------------------------
-constexpr int kCoarse = 1024;  // cells per level-1 counter (32 bitmap words)
+constexpr int kCoarse = 256;   // cells per level-1 counter (8 bitmap words = one 32-byte sector)
+constexpr int kWordsPerCoarse = kCoarse / 32;
 
 struct ConvWs {
   unsigned int* bitmap;  // cells/32 words
@@ -130,11 +131,11 @@ inline ConvWs conv_layout(void* base, unsigned long long cells, int out_capacity
   w.n_l2 = (w.n_l1 + 1023) / 1024;
   size_t off = 0;
   w.bitmap = reinterpret_cast<unsigned int*>(p + off);
-  off = align_up(off + 4 * (w.n_l1 * 32), 256);  // whole 32-word groups so R3 can read uint4s
+  off = align_up(off + 4 * (w.n_l1 * kWordsPerCoarse), 256);  // whole sectors
   w.l1 = reinterpret_cast<int*>(p + off);
   off = align_up(off + 4 * (w.n_l2 * 1024), 256);
   w.l2 = reinterpret_cast<int*>(p + off);
-  off = align_up(off + 4 * 1024, 256);
+  off = align_up(off + 4 * (w.n_l2 > 1024 ? w.n_l2 : 1024), 256);
   w.n_uniq = reinterpret_cast<int*>(p + off);
   off = align_up(off + 4, 256);
   w.zero_bytes = off;
@@ -200,11 +201,30 @@ __global__ void __launch_bounds__(1024) conv_scan_l1_kernel(ConvWs W) {
 
 __global__ void __launch_bounds__(1024) conv_scan_l2_kernel(ConvWs W, int* __restrict__ n_out) {
   __shared__ int sm[33];
-  int v = threadIdx.x < W.n_l2 ? W.l2[threadIdx.x] : 0;
-  int total;
-  int ex = block_exclusive_scan(v, sm, total);
-  if (threadIdx.x < W.n_l2) W.l2[threadIdx.x] = ex;
-  if (threadIdx.x == 0) *n_out = total;  // un-clamped: caller detects overflow as n_out > capacity
+  int carry = 0;
+  for (size_t base = 0; base < W.n_l2; base += 1024) {  // one pass for <= 268 M cells, loops beyond
+    const size_t i = base + threadIdx.x;
+    int v = i < W.n_l2 ? W.l2[i] : 0;
+    int total;
+    int ex = block_exclusive_scan(v, sm, total);
+    if (i < W.n_l2) W.l2[i] = carry + ex;
+    carry += total;
+  }
+  if (threadIdx.x == 0) *n_out = carry;  // un-clamped: caller detects overflow as n_out > capacity
+}
+
+// row of an active cell = number of active cells before it in flat order (two-level prefix + <= 1 sector
+// of popcounts); -1 if the cell is not active. This IS the site index of every level produced by a
+// strided conv (its rows are numbered in ascending flat order), so those levels need no hash table.
+__device__ __forceinline__ int rank_of_cell(const ConvWs& W, unsigned int cell) {
+  const unsigned int wq = cell >> 5;
+  const unsigned int word = __ldg(&W.bitmap[wq]);
+  const unsigned int bit = 1u << (cell & 31);
+  if (!(word & bit)) return -1;
+  const unsigned int g1 = cell / kCoarse;
+  int rank = __ldg(&W.l2[g1 >> 10]) + __ldg(&W.l1[g1]) + __popc(word & (bit - 1u));
+  for (unsigned int w = g1 * kWordsPerCoarse; w < wq; w++) rank += __popc(__ldg(&W.bitmap[w]));
+  return rank;
 }
 
 __global__ void __launch_bounds__(256) conv_rank_kernel(ConvWs W, ConvGeom G, int out_capacity,
@@ -212,12 +232,8 @@ __global__ void __launch_bounds__(256) conv_rank_kernel(ConvWs W, ConvGeom G, in
   const int n = min(*W.n_uniq, out_capacity);
   for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
     const unsigned int cell = W.uniq[u];
-    const unsigned int g1 = cell / kCoarse;
-    int rank = W.l2[g1 >> 10] + W.l1[g1];
-    const unsigned int w0 = g1 * 32, wq = cell >> 5;
-    for (unsigned int w = w0; w < wq; w++) rank += __popc(__ldg(&W.bitmap[w]));
-    rank += __popc(__ldg(&W.bitmap[wq]) & ((1u << (cell & 31)) - 1u));
-    if (rank < out_capacity) {
+    const int rank = rank_of_cell(W, cell);
+    if (rank >= 0 && rank < out_capacity) {
       unsigned int r = cell;
       int x = r % G.out_shape[2];
       r /= G.out_shape[2];
@@ -227,6 +243,34 @@ __global__ void __launch_bounds__(256) conv_rank_kernel(ConvWs W, ConvGeom G, in
       r /= G.out_shape[0];
       out_idx[rank] = make_int4((int)r, z, y, x);
     }
+  }
+}
+
+// Same contract as rule_lookup_kernel, for an INPUT level whose rows are in ascending flat order and
+// indexed by the bitmap/prefix workspace of the strided conv that produced it (no hash probes: one bitmap
+// word per candidate, and only for present neighbours one prefix pair + <= 1 sector of popcounts).
+__global__ void __launch_bounds__(256) rule_lookup_rank_kernel(ConvWs Win, const int4* __restrict__ out_idx,
+                                                               const int* __restrict__ n_out, int out_cap,
+                                                               ConvGeom G, int identity_kk,
+                                                               int* __restrict__ nbr, int nbr_stride) {
+  const int n = min(*n_out, out_cap);
+  const int kk = blockIdx.y;
+  const int kx = kk % G.ks[2], ky = (kk / G.ks[2]) % G.ks[1], kz = kk / (G.ks[2] * G.ks[1]);
+  for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n; o += gridDim.x * blockDim.x) {
+    int r;
+    if (kk == identity_kk) {
+      r = o;
+    } else {
+      int4 c = out_idx[o];
+      const int z = c.y * G.stride[0] - G.pad[0] + kz * G.dil[0];
+      const int y = c.z * G.stride[1] - G.pad[1] + ky * G.dil[1];
+      const int x = c.w * G.stride[2] - G.pad[2] + kx * G.dil[2];
+      r = -1;
+      if (z >= 0 && z < G.in_shape[0] && y >= 0 && y < G.in_shape[1] && x >= 0 && x < G.in_shape[2])
+        r = rank_of_cell(Win, (unsigned int)((((size_t)c.x * G.in_shape[0] + z) * G.in_shape[1] + y) *
+                                                 G.in_shape[2] + x));
+    }
+    nbr[(size_t)kk * nbr_stride + o] = r;
   }
 }
 
@@ -301,6 +345,30 @@ extern "C" int v3d_rulebook_subm(const void* table, const int* indices, const in
   return check_launch();
 }
 
+// SubM on a level produced by a strided conv: `level_index` is that conv's workspace (bitmap + prefix).
+extern "C" int v3d_rulebook_subm_ranked(const void* level_index, int B, int index_capacity, const int* indices,
+                                        const int* n_rows, int capacity_rows, const int* shape_host,
+                                        const int* ksize_host, const int* dilation_host, int* nbr, int nbr_stride,
+                                        v3d_stream_t stream) {
+  if (!level_index || !indices || !n_rows || !shape_host || !ksize_host || !dilation_host || !nbr)
+    return V3D_ERR_INVALID_ARGUMENT;
+  if (nbr_stride < capacity_rows || B <= 0) return V3D_ERR_INVALID_ARGUMENT;
+  for (int d = 0; d < 3; d++)
+    if (ksize_host[d] <= 0 || (ksize_host[d] & 1) == 0) return V3D_ERR_INVALID_ARGUMENT;
+  ConvGeom G;
+  int one[3] = {1, 1, 1};
+  int pad[3] = {ksize_host[0] / 2 * dilation_host[0], ksize_host[1] / 2 * dilation_host[1],
+                ksize_host[2] / 2 * dilation_host[2]};
+  fill_geom(G, shape_host, ksize_host, one, pad, dilation_host);
+  if (G.KV > 65535) return V3D_ERR_INVALID_ARGUMENT;
+  const unsigned long long cells = (unsigned long long)B * shape_host[0] * shape_host[1] * shape_host[2];
+  ConvWs Win = conv_layout(const_cast<void*>(level_index), cells, index_capacity);
+  const int centre = ((ksize_host[0] / 2) * ksize_host[1] + ksize_host[1] / 2) * ksize_host[2] + ksize_host[2] / 2;
+  rule_lookup_rank_kernel<<<dim3(row_grid(capacity_rows), G.KV), 256, 0, as_stream(stream)>>>(
+      Win, reinterpret_cast<const int4*>(indices), n_rows, capacity_rows, G, centre, nbr, nbr_stride);
+  return check_launch();
+}
+
 extern "C" void v3d_conv_out_shape(const int* shape, const int* ksize, const int* stride, const int* pad,
                                    const int* dilation, int* out_shape) {
   ConvGeom G;
@@ -316,12 +384,13 @@ extern "C" size_t v3d_rulebook_conv_workspace_bytes(int B, const int* out_shape_
   return conv_layout(nullptr, cells, capacity_rows).total;
 }
 
-extern "C" int v3d_rulebook_conv(const void* in_table, const int* indices, const int* n_rows,
-                                 int capacity_rows, int B, const int* shape_host, const int* ksize_host,
-                                 const int* stride_host, const int* pad_host, const int* dilation_host,
-                                 int* out_indices, int* n_out, int out_capacity, int* nbr, int nbr_stride,
-                                 void* workspace, size_t workspace_bytes, v3d_stream_t stream) {
-  if (!in_table || !indices || !n_rows || !shape_host || !ksize_host || !stride_host || !pad_host ||
+static int rulebook_conv_impl(const void* in_table, const void* in_level_index, int in_index_capacity,
+                              const int* indices, const int* n_rows, int capacity_rows, int B,
+                              const int* shape_host, const int* ksize_host, const int* stride_host,
+                              const int* pad_host, const int* dilation_host, int* out_indices, int* n_out,
+                              int out_capacity, int* nbr, int nbr_stride, void* workspace, size_t workspace_bytes,
+                              v3d_stream_t stream) {
+  if ((!in_table && !in_level_index) || !indices || !n_rows || !shape_host || !ksize_host || !stride_host || !pad_host ||
       !dilation_host || !out_indices || !n_out || !nbr || !workspace)
     return V3D_ERR_INVALID_ARGUMENT;
   if (B <= 0 || out_capacity <= 0 || nbr_stride < out_capacity) return V3D_ERR_INVALID_ARGUMENT;
@@ -331,10 +400,9 @@ extern "C" int v3d_rulebook_conv(const void* in_table, const int* indices, const
     if (G.out_shape[d] <= 0 || stride_host[d] <= 0) return V3D_ERR_INVALID_ARGUMENT;
   if (G.KV > 65535) return V3D_ERR_INVALID_ARGUMENT;
   unsigned long long cells = (unsigned long long)B * G.out_shape[0] * G.out_shape[1] * G.out_shape[2];
-  if (cells >= (1ull << 30)) return V3D_ERR_INVALID_ARGUMENT;  // level-2 scan is one 1024-thread block
+  if (cells >= (1ull << 32)) return V3D_ERR_INVALID_ARGUMENT;  // cell ids are 32-bit
   ConvWs W = conv_layout(workspace, cells, out_capacity);
   if (workspace_bytes < W.total) return V3D_ERR_WORKSPACE_TOO_SMALL;
-  SiteTable T = table_layout(const_cast<void*>(in_table), capacity_rows);
   cudaStream_t st = as_stream(stream);
   V3D_CUDA_TRY(cudaMemsetAsync(workspace, 0, W.zero_bytes, st));
   conv_mark_kernel<<<dim3(row_grid(capacity_rows), G.KV), 256, 0, st>>>(
@@ -343,7 +411,38 @@ extern "C" int v3d_rulebook_conv(const void* in_table, const int* indices, const
   conv_scan_l2_kernel<<<1, 1024, 0, st>>>(W, n_out);
   conv_rank_kernel<<<row_grid(out_capacity), 256, 0, st>>>(W, G, out_capacity,
                                                           reinterpret_cast<int4*>(out_indices));
-  rule_lookup_kernel<<<dim3(row_grid(out_capacity), G.KV), 256, 0, st>>>(
-      T, reinterpret_cast<const int4*>(out_indices), n_out, out_capacity, G, -1, nbr, nbr_stride);
+  if (in_level_index) {
+    const unsigned long long in_cells = (unsigned long long)B * shape_host[0] * shape_host[1] * shape_host[2];
+    ConvWs Win = conv_layout(const_cast<void*>(in_level_index), in_cells, in_index_capacity);
+    rule_lookup_rank_kernel<<<dim3(row_grid(out_capacity), G.KV), 256, 0, st>>>(
+        Win, reinterpret_cast<const int4*>(out_indices), n_out, out_capacity, G, -1, nbr, nbr_stride);
+  } else {
+    SiteTable T = table_layout(const_cast<void*>(in_table), capacity_rows);
+    rule_lookup_kernel<<<dim3(row_grid(out_capacity), G.KV), 256, 0, st>>>(
+        T, reinterpret_cast<const int4*>(out_indices), n_out, out_capacity, G, -1, nbr, nbr_stride);
+  }
   return check_launch();
+}
+
+extern "C" int v3d_rulebook_conv(const void* in_table, const int* indices, const int* n_rows,
+                                 int capacity_rows, int B, const int* shape_host, const int* ksize_host,
+                                 const int* stride_host, const int* pad_host, const int* dilation_host,
+                                 int* out_indices, int* n_out, int out_capacity, int* nbr, int nbr_stride,
+                                 void* workspace, size_t workspace_bytes, v3d_stream_t stream) {
+  return rulebook_conv_impl(in_table, nullptr, 0, indices, n_rows, capacity_rows, B, shape_host, ksize_host,
+                            stride_host, pad_host, dilation_host, out_indices, n_out, out_capacity, nbr, nbr_stride,
+                            workspace, workspace_bytes, stream);
+}
+
+// Strided conv whose INPUT level was itself produced by a strided conv: `in_level_index` is that conv's
+// workspace (its capacity = in_index_capacity); no hash table is involved.
+extern "C" int v3d_rulebook_conv_ranked(const void* in_level_index, int in_index_capacity, const int* indices,
+                                        const int* n_rows, int capacity_rows, int B, const int* shape_host,
+                                        const int* ksize_host, const int* stride_host, const int* pad_host,
+                                        const int* dilation_host, int* out_indices, int* n_out, int out_capacity,
+                                        int* nbr, int nbr_stride, void* workspace, size_t workspace_bytes,
+                                        v3d_stream_t stream) {
+  return rulebook_conv_impl(nullptr, in_level_index, in_index_capacity, indices, n_rows, capacity_rows, B, shape_host,
+                            ksize_host, stride_host, pad_host, dilation_host, out_indices, n_out, out_capacity, nbr,
+                            nbr_stride, workspace, workspace_bytes, stream);
 }

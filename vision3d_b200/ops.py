@@ -192,10 +192,22 @@ def conv_out_shape(shape, ksize, stride, padding, dilation):
     return [int(x) for x in out]
 
 
-def rulebook_subm(table, indices, n_rows, shape, ksize, dilation, nbr=None):
-    """nbr (KV, capacity) int32: nbr[kk, o] = input row or -1. Outputs == inputs."""
+def rulebook_subm(table, indices, n_rows, shape, ksize, dilation, nbr=None, capacity=None):
+    """nbr (KV, capacity) int32: nbr[kk, o] = input row or -1. Outputs == inputs.
+    `table` is a SiteTable (hash) or the ConvRulebookWorkspace of the strided conv that produced the level."""
     ks, dl = _triple(ksize), _triple(dilation)
     kv = ks[0] * ks[1] * ks[2]
+    if isinstance(table, ConvRulebookWorkspace):
+        cap = int(capacity if capacity is not None else table.capacity)
+        if nbr is None:
+            nbr = torch.empty((kv, cap), dtype=_I32, device=indices.device)
+        assert list(shape) == table.shape
+        with torch.cuda.device(indices.device):
+            check(_lib.load().v3d_rulebook_subm_ranked(table.buf.data_ptr(), table.batch_size, table.capacity,
+                                                       indices.data_ptr(), n_rows.data_ptr(), cap, i3(shape),
+                                                       i3(ks), i3(dl), nbr.data_ptr(), nbr.shape[1], _stream()),
+                  "v3d_rulebook_subm_ranked")
+        return nbr
     cap = table.capacity
     if nbr is None:
         nbr = torch.empty((kv, cap), dtype=_I32, device=indices.device)
@@ -207,7 +219,11 @@ def rulebook_subm(table, indices, n_rows, shape, ksize, dilation, nbr=None):
 
 
 class ConvRulebookWorkspace:
+    """Workspace of one strided rule-book build. After the call it doubles as the SITE INDEX of the output
+    level (bitmap + popcount prefix; rows are in ascending flat order), see rulebook_subm(level_index=...)."""
+
     def __init__(self, batch_size, out_shape, out_capacity, kernel_volume, device):
+        self.batch_size, self.shape, self.capacity = int(batch_size), [int(v) for v in out_shape], int(out_capacity)
         nbytes = _lib.load().v3d_rulebook_conv_workspace_bytes(int(batch_size), i3(out_shape), int(out_capacity),
                                                                int(kernel_volume))
         self.buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
@@ -227,6 +243,15 @@ def rulebook_conv(in_table, indices, n_rows, batch_size, shape, ksize, stride, p
         nbr = torch.empty((kv, out_capacity), dtype=_I32, device=dev)
     if workspace is None:
         workspace = ConvRulebookWorkspace(batch_size, out_shape, out_capacity, kv, dev)
+    if isinstance(in_table, ConvRulebookWorkspace):  # input level indexed by the conv that produced it
+        assert list(shape) == in_table.shape and int(batch_size) == in_table.batch_size
+        with torch.cuda.device(dev):
+            check(_lib.load().v3d_rulebook_conv_ranked(
+                in_table.buf.data_ptr(), in_table.capacity, indices.data_ptr(), n_rows.data_ptr(),
+                int(indices.shape[0]), int(batch_size), i3(shape), i3(ks), i3(st), i3(pd), i3(dl),
+                out_indices.data_ptr(), n_out.data_ptr(), int(out_capacity), nbr.data_ptr(), nbr.shape[1],
+                workspace.buf.data_ptr(), workspace.buf.numel(), _stream()), "v3d_rulebook_conv_ranked")
+        return out_indices, n_out, nbr, out_shape
     with torch.cuda.device(dev):
         check(_lib.load().v3d_rulebook_conv(
             in_table.buf.data_ptr(), indices.data_ptr(), n_rows.data_ptr(), in_table.capacity, int(batch_size),

@@ -346,7 +346,7 @@ class SecondEngine:
         for lv in range(1, 5):
             self.n_rows.append(torch.zeros(1, dtype=torch.int32, device=dev))
             self.indices.append(torch.zeros((self.caps[lv], 4), dtype=torch.int32, device=dev))
-        self.tables = [ops.SiteTable(self.caps[lv], dev) for lv in range(4)]
+        self.tables = [ops.SiteTable(self.caps[0], dev)]  # only level 0 needs a hash (see _build_plan)
         self.nbr_subm = [torch.empty((27, self.caps[lv]), dtype=torch.int32, device=dev) for lv in range(4)]
         self.nbr_conv, self.conv_ws = [], []
         for lv in range(4):
@@ -416,10 +416,18 @@ class SecondEngine:
         x = self.vox_out["mean"]
         li = 0
         for lv in range(4):
-            plan.append(("site_table_L%d" % lv, 2, (lambda lv=lv: self.tables[lv].build(
-                self.indices[lv], self.n_rows[lv], self.shapes[lv]))))
-            plan.append(("rulebook_subm_L%d" % lv, 1, (lambda lv=lv: ops.rulebook_subm(
-                self.tables[lv], self.indices[lv], self.n_rows[lv], self.shapes[lv], 3, 1, self.nbr_subm[lv]))))
+            if lv == 0:
+                # voxel rows are in first-appearance order: level 0 needs the hash site table
+                plan.append(("site_table_L0", 2, (lambda: self.tables[0].build(
+                    self.indices[0], self.n_rows[0], self.shapes[0]))))
+                index = self.tables[0]
+            else:
+                # levels produced by a strided conv are in ascending flat order: that conv's bitmap +
+                # popcount prefix IS their site index (no hash build, no hash probes)
+                index = self.conv_ws[lv - 1]
+            plan.append(("rulebook_subm_L%d" % lv, 1, (lambda lv=lv, index=index: ops.rulebook_subm(
+                index, self.indices[lv], self.n_rows[lv], self.shapes[lv], 3, 1, self.nbr_subm[lv],
+                capacity=self.caps[lv]))))
             # level input lives in `mean` (level 0) or in feat[lv][0] (written by the strided conv that
             # entered the level); SubM layers ping-pong between the level's two buffers
             cur = 0 if lv == 0 else 1
@@ -433,8 +441,8 @@ class SecondEngine:
                                  d["shift"], True, out=out))))
                 x, cur, li, k = out, cur ^ 1, li + 1, k + 1
             d, out = self.layers[li], self.feat[lv + 1][0]
-            plan.append(("rulebook_conv_L%d" % lv, 5, (lambda d=d, lv=lv: ops.rulebook_conv(
-                self.tables[lv], self.indices[lv], self.n_rows[lv], B, self.shapes[lv], d["ks"], d["stride"],
+            plan.append(("rulebook_conv_L%d" % lv, 5, (lambda d=d, lv=lv, index=index: ops.rulebook_conv(
+                index, self.indices[lv], self.n_rows[lv], B, self.shapes[lv], d["ks"], d["stride"],
                 d["pad"], d["dil"], self.caps[lv + 1], self.indices[lv + 1], self.n_rows[lv + 1],
                 self.nbr_conv[lv], self.conv_ws[lv]))))
             plan.append(("sconv_L%d_%dx%d" % (lv, d["cin"], d["cout"]), 1,
