@@ -5,9 +5,9 @@
 // One persistent CTA per SM, warp specialised (448 threads):
 //   warps 0-3  epilogue   : tcgen05.ld the 128 x COUT fp32 accumulator (lane = output row), apply
 //                           scale/shift/ReLU, store each output row once
-//   warp  4    MMA issuer : one elected thread; per pipeline slot issues 3*(CIN/8) tcgen05.mma
-//                           (A_lo*B_hi + A_hi*B_lo + A_hi*B_hi) M=128, N=COUT, K=8 with A read from
-//                           TMEM and B from shared memory; tcgen05.commit frees the A stage, the B
+//   warp  4    MMA issuer : warp-uniform loop, one elected lane issues per pipeline slot 2*(CIN/8)
+//                           tcgen05.mma with A from TMEM and B from shared memory, K=8:
+//                           A_hi*[B_hi|B_lo] (M=128, N=2*COUT) and A_lo*B_hi (N=COUT); tcgen05.commit frees the A stage, the B
 //                           stage and publishes the accumulator through mbarriers
 //   warp  5    weight TMA : finds the kernel offsets each tile uses and streams the pre-swizzled,
 //                           pre-split W[kk] images (hi+lo) with cp.async.bulk (1-D TMA) into a deep
@@ -143,12 +143,14 @@ struct TcCfg {
   static constexpr int kChunks = (CIN + 31) / 32;
   static constexpr int kKSteps = CIN / 8;
   static constexpr int kUnitsPerRow = CIN / 4;                // float4 loads per gathered row
-  static constexpr int kBChunkBytes = COUT * 128;
-  static constexpr int kBPartBytes = kChunks * kBChunkBytes;  // hi or lo
-  static constexpr int kBBytes = 2 * kBPartBytes;             // == one prepared W[kk] image
+  // one B chunk = 2*COUT rows x 128 B: rows [0, COUT) hold W_hi^T, rows [COUT, 2*COUT) hold W_lo^T, so that
+  // ONE N = 2*COUT MMA computes A_hi*[B_hi | B_lo] (the gathered operand is fetched once for both products)
+  static constexpr int kBChunkBytes = 2 * COUT * 128;
+  static constexpr int kBBytes = kChunks * kBChunkBytes;      // == one prepared W[kk] image
   static constexpr int kBStagesFit = (160 * 1024) / kBBytes;
   static constexpr int kBStages = kBStagesFit > 8 ? 8 : kBStagesFit;
-  static constexpr int kAccCols = 2 * COUT;
+  static constexpr int kAccBufCols = 2 * COUT;                // [A_hi*B_hi + A_lo*B_hi | A_hi*B_lo]
+  static constexpr int kAccCols = 2 * kAccBufCols;            // double buffered
   static constexpr int kAStageCols = 2 * CIN;                 // hi | lo
   static constexpr int kAStagesFit = (512 - kAccCols) / kAStageCols;
   static constexpr int kAStages = kAStagesFit > 4 ? 4 : kAStagesFit;
@@ -233,18 +235,28 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
       mbar_wait(&acc_full[a], (it >> 1) & 1);
       tc_fence_after();
       const int row = tile * kTileM + warp * 32 + lane;
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * COUT);
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * C::kAccBufCols);
       float* orow = out + (size_t)row * COUT;
 #pragma unroll
       for (int c0 = 0; c0 < COUT; c0 += 16) {
-        uint32_t v[16];
+        uint32_t v[16], v2[16];
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
             "%14, %15}, [%16];"
             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
               "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
             : "r"(taddr + (uint32_t)c0));
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
+            "%14, %15}, [%16];"
+            : "=r"(v2[0]), "=r"(v2[1]), "=r"(v2[2]), "=r"(v2[3]), "=r"(v2[4]), "=r"(v2[5]), "=r"(v2[6]), "=r"(v2[7]),
+              "=r"(v2[8]), "=r"(v2[9]), "=r"(v2[10]), "=r"(v2[11]), "=r"(v2[12]), "=r"(v2[13]), "=r"(v2[14]),
+              "=r"(v2[15])
+            : "r"(taddr + (uint32_t)(COUT + c0)));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int e = 0; e < 16; e++)  // (A_hi*B_hi + A_lo*B_hi) + A_hi*B_lo
+          v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(v2[e]));
         if (c0 + 16 >= COUT) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
           tc_fence_before();
           mbar_arrive(&acc_empty[a]);
@@ -275,7 +287,7 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
     // single divergent thread every UTCHMMA needed ELECT + R2UR moves: ~380 SASS instructions and ~2500
     // clk of issue time per slot, three times the 768 clk the tensor pipe needs.)
     {
-      constexpr uint32_t idesc = make_idesc(kTileM, COUT);
+      constexpr uint32_t idesc_wide = make_idesc(kTileM, 2 * COUT), idesc_hi = make_idesc(kTileM, COUT);
       const uint32_t b_ring = smem_u32(bring);
       uint32_t q = 0;
       int it = 0;
@@ -298,18 +310,16 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
           }
           mbar_wait(&full_b[bs], (q / C::kBStages) & 1u);
           tc_fence_after();
-          const uint32_t b_hi = b_ring + bs * (uint32_t)C::kBBytes;
-          const uint64_t dbh0 = make_desc(b_hi), dbl0 = make_desc(b_hi + (uint32_t)C::kBPartBytes);
+          const uint64_t db0 = make_desc(b_ring + bs * (uint32_t)C::kBBytes);
           const uint32_t a_hi = tmem_base + (uint32_t)(C::kAccCols + as * C::kAStageCols), a_lo = a_hi + CIN;
-          const uint32_t d = tmem_base + (uint32_t)(a * COUT);
+          const uint32_t d = tmem_base + (uint32_t)(a * C::kAccBufCols);
           if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < C::kKSteps; ks++) {
               // descriptor start address advances in 16-byte units (low 14 bits of the descriptor)
-              const uint64_t bo = (uint64_t)(((ks >> 2) * C::kBChunkBytes + (ks & 3) * 32) >> 4);
-              umma_tf32_ts(d, a_lo + 8u * ks, dbh0 + bo, idesc, accum);  // small terms first
-              umma_tf32_ts(d, a_hi + 8u * ks, dbl0 + bo, idesc, 1u);
-              umma_tf32_ts(d, a_hi + 8u * ks, dbh0 + bo, idesc, 1u);
+              const uint64_t db = db0 + (uint64_t)(((ks >> 2) * C::kBChunkBytes + (ks & 3) * 32) >> 4);
+              umma_tf32_ts(d, a_hi + 8u * ks, db, idesc_wide, accum);  // A_hi * [B_hi | B_lo], N = 2*COUT
+              umma_tf32_ts(d, a_lo + 8u * ks, db, idesc_hi, 1u);       // A_lo * B_hi into the first COUT columns
               accum = 1u;
             }
             umma_commit(&empty_a[as]);  // stages reusable once these MMAs have read them
@@ -532,7 +542,7 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
 __global__ void prepare_weights_kernel(const float* __restrict__ w, int KV, int Cin, int Cout,
                                        unsigned char* __restrict__ img) {
   const int chunks = (Cin + 31) / 32;
-  const size_t part = (size_t)chunks * Cout * 128, per_kk = 2 * part;
+  const size_t chunk_bytes = (size_t)2 * Cout * 128, per_kk = chunks * chunk_bytes;
   const int total = KV * Cout * chunks * 32;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
     const int kl = e % 32;
@@ -544,10 +554,12 @@ __global__ void prepare_weights_kernel(const float* __restrict__ w, int KV, int 
     const float v = k < Cin ? w[((size_t)kk * Cin + k) * Cout + n] : 0.f;
     const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
     const float lo = v - hi;
-    const size_t off = (size_t)ch * Cout * 128 + (size_t)(n >> 3) * 1024 + (size_t)(n & 7) * 128 +
+    // chunk-major; inside a chunk rows [0,Cout) = hi, rows [Cout, 2*Cout) = lo (Cout is a multiple of 8, so the
+    // lo rows start on an 8-row group boundary and keep the same (row & 7) swizzle phase)
+    const size_t off = (size_t)ch * chunk_bytes + (size_t)(n >> 3) * 1024 + (size_t)(n & 7) * 128 +
                        (size_t)((((kl >> 2) ^ (n & 7)) << 4) + (kl & 3) * 4);
     *reinterpret_cast<float*>(img + (size_t)kk * per_kk + off) = hi;
-    *reinterpret_cast<float*>(img + (size_t)kk * per_kk + part + off) = lo;
+    *reinterpret_cast<float*>(img + (size_t)kk * per_kk + (size_t)Cout * 128 + off) = lo;
   }
 }
 
