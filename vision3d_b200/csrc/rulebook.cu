@@ -81,30 +81,38 @@ __global__ void __launch_bounds__(256) rule_lookup_kernel(SiteTable T, const int
                                                           ConvGeom G, int identity_kk,
                                                           int* __restrict__ nbr, int nbr_stride) {
   const int n = min(*n_out, out_cap);
-  const int kk = blockIdx.y;
-  const int kx = kk % G.ks[2], ky = (kk / G.ks[2]) % G.ks[1], kz = kk / (G.ks[2] * G.ks[1]);
   const unsigned int calls = T.hdr->epoch;
   const unsigned int epoch = epoch24(calls);
   Shape3 ish{{G.in_shape[0], G.in_shape[1], G.in_shape[2]}};
+  // one thread per output row walks all kernel offsets (coordinates loaded once; for a fixed offset
+  // consecutive threads write consecutive nbr entries)
   for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n; o += gridDim.x * blockDim.x) {
-    int r;
-    if (kk == identity_kk) {
-      r = o;
-    } else {
-      int4 c = out_idx[o];
+    const int4 c = out_idx[o];
+    int kk = 0;
+    for (int kz = 0; kz < G.ks[0]; kz++) {
       const int z = c.y * G.stride[0] - G.pad[0] + kz * G.dil[0];
-      const int y = c.z * G.stride[1] - G.pad[1] + ky * G.dil[1];
-      const int x = c.w * G.stride[2] - G.pad[2] + kx * G.dil[2];
-      r = -1;
-      if (z >= 0 && z < G.in_shape[0] && y >= 0 && y < G.in_shape[1] && x >= 0 && x < G.in_shape[2]) {
-        unsigned int s = table_find(T.keys, T.cap - 1, epoch, flat_key(c.x, z, y, x, ish));
-        if (s != 0xFFFFFFFFu) {
-          const unsigned long long v = __ldg(&T.vals[s]);
-          if ((unsigned int)(v >> 32) == calls) r = (int)(unsigned int)v;  // else: stale alias, not a site
+      for (int ky = 0; ky < G.ks[1]; ky++) {
+        const int y = c.z * G.stride[1] - G.pad[1] + ky * G.dil[1];
+        const bool zy_ok = z >= 0 && z < G.in_shape[0] && y >= 0 && y < G.in_shape[1];
+        for (int kx = 0; kx < G.ks[2]; kx++, kk++) {
+          int r;
+          if (kk == identity_kk) {
+            r = o;
+          } else {
+            const int x = c.w * G.stride[2] - G.pad[2] + kx * G.dil[2];
+            r = -1;
+            if (zy_ok && x >= 0 && x < G.in_shape[2]) {
+              unsigned int s = table_find(T.keys, T.cap - 1, epoch, flat_key(c.x, z, y, x, ish));
+              if (s != 0xFFFFFFFFu) {
+                const unsigned long long v = __ldg(&T.vals[s]);
+                if ((unsigned int)(v >> 32) == calls) r = (int)(unsigned int)v;  // else: stale alias, not a site
+              }
+            }
+          }
+          nbr[(size_t)kk * nbr_stride + o] = r;
         }
       }
     }
-    nbr[(size_t)kk * nbr_stride + o] = r;
   }
 }
 
@@ -149,40 +157,47 @@ __global__ void __launch_bounds__(256) conv_mark_kernel(const int4* __restrict__
                                                         const int* __restrict__ n_rows, int cap_rows,
                                                         ConvGeom G, ConvWs W, int out_capacity) {
   const int n = min(*n_rows, cap_rows);
-  const int kk = blockIdx.y;
-  const int kx = kk % G.ks[2], ky = (kk / G.ks[2]) % G.ks[1], kz = kk / (G.ks[2] * G.ks[1]);
   const int lane = threadIdx.x & 31;
-  // warp-uniform trip count so that the append below can be aggregated with one atomic per warp
+  // one thread per input row walks the kernel offsets (only ~1/stride^3 of them reach an output cell);
+  // warp-uniform trip counts so that the append can be aggregated with one atomic per warp and offset
   for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += gridDim.x * blockDim.x) {
     const int i = i0 + lane;
-    bool fresh = false;
-    unsigned int cell = 0;
-    if (i < n) {
-      int4 c = idx[i];
-      int nz = c.y + G.pad[0] - kz * G.dil[0];
-      int ny = c.z + G.pad[1] - ky * G.dil[1];
-      int nx = c.w + G.pad[2] - kx * G.dil[2];
-      bool ok = nz >= 0 && ny >= 0 && nx >= 0 && !(nz % G.stride[0]) && !(ny % G.stride[1]) && !(nx % G.stride[2]);
-      int oz = nz / G.stride[0], oy = ny / G.stride[1], ox = nx / G.stride[2];
-      ok = ok && oz < G.out_shape[0] && oy < G.out_shape[1] && ox < G.out_shape[2];
-      if (ok) {
-        cell = (unsigned int)((((size_t)c.x * G.out_shape[0] + oz) * G.out_shape[1] + oy) * G.out_shape[2] + ox);
-        const unsigned int bit = 1u << (cell & 31);
-        const unsigned int old = atomicOr(&W.bitmap[cell >> 5], bit);
-        if (!(old & bit)) {
-          fresh = true;
-          atomicAdd(&W.l1[cell / kCoarse], 1);
+    const int4 c = i < n ? idx[i] : make_int4(0, 0, 0, 0);
+    for (int kz = 0; kz < G.ks[0]; kz++) {
+      const int nz = c.y + G.pad[0] - kz * G.dil[0];
+      const int oz = nz / G.stride[0];
+      const bool z_ok = nz >= 0 && (nz - oz * G.stride[0]) == 0 && oz < G.out_shape[0];
+      for (int ky = 0; ky < G.ks[1]; ky++) {
+        const int ny = c.z + G.pad[1] - ky * G.dil[1];
+        const int oy = ny / G.stride[1];
+        const bool zy_ok = z_ok && ny >= 0 && (ny - oy * G.stride[1]) == 0 && oy < G.out_shape[1];
+        if (!__any_sync(0xffffffffu, zy_ok && i < n)) continue;  // warp-uniform skip
+        for (int kx = 0; kx < G.ks[2]; kx++) {
+          const int nx = c.w + G.pad[2] - kx * G.dil[2];
+          const int ox = nx / G.stride[2];
+          const bool ok = i < n && zy_ok && nx >= 0 && (nx - ox * G.stride[2]) == 0 && ox < G.out_shape[2];
+          bool fresh = false;
+          unsigned int cell = 0;
+          if (ok) {
+            cell = (unsigned int)((((size_t)c.x * G.out_shape[0] + oz) * G.out_shape[1] + oy) * G.out_shape[2] + ox);
+            const unsigned int bit = 1u << (cell & 31);
+            const unsigned int old = atomicOr(&W.bitmap[cell >> 5], bit);
+            if (!(old & bit)) {
+              fresh = true;
+              atomicAdd(&W.l1[cell / kCoarse], 1);
+            }
+          }
+          const unsigned int m = __ballot_sync(0xffffffffu, fresh);
+          if (m) {
+            int base = 0;
+            if (lane == (__ffs(m) - 1)) base = atomicAdd(W.n_uniq, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+            if (fresh) {
+              const int u = base + __popc(m & ((1u << lane) - 1u));
+              if (u < out_capacity) W.uniq[u] = cell;
+            }
+          }
         }
-      }
-    }
-    const unsigned int m = __ballot_sync(0xffffffffu, fresh);
-    if (m) {
-      int base = 0;
-      if (lane == (__ffs(m) - 1)) base = atomicAdd(W.n_uniq, __popc(m));
-      base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-      if (fresh) {
-        const int u = base + __popc(m & ((1u << lane) - 1u));
-        if (u < out_capacity) W.uniq[u] = cell;
       }
     }
   }
@@ -254,23 +269,30 @@ __global__ void __launch_bounds__(256) rule_lookup_rank_kernel(ConvWs Win, const
                                                                ConvGeom G, int identity_kk,
                                                                int* __restrict__ nbr, int nbr_stride) {
   const int n = min(*n_out, out_cap);
-  const int kk = blockIdx.y;
-  const int kx = kk % G.ks[2], ky = (kk / G.ks[2]) % G.ks[1], kz = kk / (G.ks[2] * G.ks[1]);
+  // one thread per output row walks all kernel offsets: the row's coordinates are loaded once, neighbours
+  // along x share bitmap words (L1 hits), and for a fixed offset consecutive threads still write
+  // consecutive nbr entries
   for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n; o += gridDim.x * blockDim.x) {
-    int r;
-    if (kk == identity_kk) {
-      r = o;
-    } else {
-      int4 c = out_idx[o];
+    const int4 c = out_idx[o];
+    int kk = 0;
+    for (int kz = 0; kz < G.ks[0]; kz++) {
       const int z = c.y * G.stride[0] - G.pad[0] + kz * G.dil[0];
-      const int y = c.z * G.stride[1] - G.pad[1] + ky * G.dil[1];
-      const int x = c.w * G.stride[2] - G.pad[2] + kx * G.dil[2];
-      r = -1;
-      if (z >= 0 && z < G.in_shape[0] && y >= 0 && y < G.in_shape[1] && x >= 0 && x < G.in_shape[2])
-        r = rank_of_cell(Win, (unsigned int)((((size_t)c.x * G.in_shape[0] + z) * G.in_shape[1] + y) *
-                                                 G.in_shape[2] + x));
+      for (int ky = 0; ky < G.ks[1]; ky++) {
+        const int y = c.z * G.stride[1] - G.pad[1] + ky * G.dil[1];
+        const bool zy_ok = z >= 0 && z < G.in_shape[0] && y >= 0 && y < G.in_shape[1];
+        const size_t row_base = (((size_t)c.x * G.in_shape[0] + z) * G.in_shape[1] + y) * G.in_shape[2];
+        for (int kx = 0; kx < G.ks[2]; kx++, kk++) {
+          int r;
+          if (kk == identity_kk) {
+            r = o;
+          } else {
+            const int x = c.w * G.stride[2] - G.pad[2] + kx * G.dil[2];
+            r = (zy_ok && x >= 0 && x < G.in_shape[2]) ? rank_of_cell(Win, (unsigned int)(row_base + x)) : -1;
+          }
+          nbr[(size_t)kk * nbr_stride + o] = r;
+        }
+      }
     }
-    nbr[(size_t)kk * nbr_stride + o] = r;
   }
 }
 
@@ -339,7 +361,7 @@ extern "C" int v3d_rulebook_subm(const void* table, const int* indices, const in
   if (G.KV > 65535) return V3D_ERR_INVALID_ARGUMENT;
   const int centre = ((ksize_host[0] / 2) * ksize_host[1] + ksize_host[1] / 2) * ksize_host[2] +
                      ksize_host[2] / 2;
-  dim3 grid(row_grid(capacity_rows), G.KV);
+  dim3 grid(row_grid(capacity_rows));
   rule_lookup_kernel<<<grid, 256, 0, as_stream(stream)>>>(T, reinterpret_cast<const int4*>(indices), n_rows,
                                                           capacity_rows, G, centre, nbr, nbr_stride);
   return check_launch();
@@ -364,7 +386,7 @@ extern "C" int v3d_rulebook_subm_ranked(const void* level_index, int B, int inde
   const unsigned long long cells = (unsigned long long)B * shape_host[0] * shape_host[1] * shape_host[2];
   ConvWs Win = conv_layout(const_cast<void*>(level_index), cells, index_capacity);
   const int centre = ((ksize_host[0] / 2) * ksize_host[1] + ksize_host[1] / 2) * ksize_host[2] + ksize_host[2] / 2;
-  rule_lookup_rank_kernel<<<dim3(row_grid(capacity_rows), G.KV), 256, 0, as_stream(stream)>>>(
+  rule_lookup_rank_kernel<<<dim3(row_grid(capacity_rows)), 256, 0, as_stream(stream)>>>(
       Win, reinterpret_cast<const int4*>(indices), n_rows, capacity_rows, G, centre, nbr, nbr_stride);
   return check_launch();
 }
@@ -405,7 +427,7 @@ static int rulebook_conv_impl(const void* in_table, const void* in_level_index, 
   if (workspace_bytes < W.total) return V3D_ERR_WORKSPACE_TOO_SMALL;
   cudaStream_t st = as_stream(stream);
   V3D_CUDA_TRY(cudaMemsetAsync(workspace, 0, W.zero_bytes, st));
-  conv_mark_kernel<<<dim3(row_grid(capacity_rows), G.KV), 256, 0, st>>>(
+  conv_mark_kernel<<<dim3(row_grid(capacity_rows)), 256, 0, st>>>(
       reinterpret_cast<const int4*>(indices), n_rows, capacity_rows, G, W, out_capacity);
   conv_scan_l1_kernel<<<(unsigned int)W.n_l2, 1024, 0, st>>>(W);
   conv_scan_l2_kernel<<<1, 1024, 0, st>>>(W, n_out);
@@ -414,11 +436,11 @@ static int rulebook_conv_impl(const void* in_table, const void* in_level_index, 
   if (in_level_index) {
     const unsigned long long in_cells = (unsigned long long)B * shape_host[0] * shape_host[1] * shape_host[2];
     ConvWs Win = conv_layout(const_cast<void*>(in_level_index), in_cells, in_index_capacity);
-    rule_lookup_rank_kernel<<<dim3(row_grid(out_capacity), G.KV), 256, 0, st>>>(
+    rule_lookup_rank_kernel<<<dim3(row_grid(out_capacity)), 256, 0, st>>>(
         Win, reinterpret_cast<const int4*>(out_indices), n_out, out_capacity, G, -1, nbr, nbr_stride);
   } else {
     SiteTable T = table_layout(const_cast<void*>(in_table), capacity_rows);
-    rule_lookup_kernel<<<dim3(row_grid(out_capacity), G.KV), 256, 0, st>>>(
+    rule_lookup_kernel<<<dim3(row_grid(out_capacity)), 256, 0, st>>>(
         T, reinterpret_cast<const int4*>(out_indices), n_out, out_capacity, G, -1, nbr, nbr_stride);
   }
   return check_launch();
