@@ -470,3 +470,13 @@ def test_rank_indexed_rulebooks_match_hash_and_oracle(cuda):
     assert sh2 == shape2 and int(n2.item()) == len(o2)
     assert np.array_equal(out2[:len(o2)].cpu().numpy(), o2)
     assert np.array_equal(nbr2[:, :len(o2)].cpu().numpy(), nbr2_want)
+
+
+def test_voxelize_large_frame_uses_global_hash_path(cuda):
+    """Frames above 32768 points take the multi-kernel global-hash path (the cluster/DSMEM kernel covers
+    frames up to 32768 points); both must give the oracle's result."""
+    big = np.concatenate([synth.make_cloud(40, 16384), synth.make_cloud(41, 16384), synth.make_cloud(42, 8000)], 0)
+    clouds = [big, synth.make_cloud(43, 2000)]
+    _check_voxelize(_run_voxelize(cuda, clouds, 60000, 0), clouds, 60000, 0)
+    mid = [np.concatenate([synth.make_cloud(44, 16384), synth.make_cloud(45, 9000)], 0)]  # PPT = 4 cluster path
+    _check_voxelize(_run_voxelize(cuda, mid, 60000, 1), mid, 60000, 1)
