@@ -480,3 +480,26 @@ def test_voxelize_large_frame_uses_global_hash_path(cuda):
     _check_voxelize(_run_voxelize(cuda, clouds, 60000, 0), clouds, 60000, 0)
     mid = [np.concatenate([synth.make_cloud(44, 16384), synth.make_cloud(45, 9000)], 0)]  # PPT = 4 cluster path
     _check_voxelize(_run_voxelize(cuda, mid, 60000, 1), mid, 60000, 1)
+
+
+def test_voxelize_cluster_dsmem_variant_subprocess(cuda):
+    """The opt-in single-kernel cluster/DSMEM voxelizer (V3D_VOXELIZE_CLUSTER=1, read once per process) must
+    give the same bit-exact result as the default path; run it in a child process."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import torch\n"
+        "from tests.test_gpu_parity import _run_voxelize, _check_voxelize\n"
+        "from vision3d_b200 import synth\n"
+        "dev = torch.device('cuda:0')\n"
+        "clouds = [synth.make_cloud(1, 5000), np.zeros((0, 4), np.float32), synth.make_cloud(2, 16384), synth.make_cloud(3, 1025)]\n"
+        "clouds[2][:4000] = clouds[2][4000:8000]\n"
+        "for pol, mv in ((0, 20000), (1, 20000), (0, 2500), (1, 2500)):\n"
+        "    _check_voxelize(_run_voxelize(dev, clouds, mv, pol), clouds, mv, pol)\n"
+        "print('cluster-ok')\n" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                    os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, V3D_VOXELIZE_CLUSTER="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert "cluster-ok" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]

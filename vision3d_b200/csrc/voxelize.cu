@@ -21,6 +21,7 @@
 // The hash table is epoch tagged (common.cuh), so nothing is cleared between calls.
 #include <cooperative_groups.h>
 #include <limits.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -209,7 +210,8 @@ template <bool kVec4>
 __global__ void __launch_bounds__(kChunk) vox_scatter_kernel(const float* __restrict__ points,
                                                              const int* __restrict__ frame_off,
                                                              VoxParams P, VoxWs W, float* __restrict__ voxels,
-                                                             int* __restrict__ num_points) {
+                                                             int* __restrict__ num_points,
+                                                             float* __restrict__ mean) {
   const int b = blockIdx.y;
   const int start = frame_off[b], n = frame_off[b + 1] - start;
   const int il = blockIdx.x * kChunk + threadIdx.x;
@@ -225,9 +227,21 @@ __global__ void __launch_bounds__(kChunk) vox_scatter_kernel(const float* __rest
   // walk the cell's list: rank = members with a smaller index; the opener also needs the
   // member count (below the cut) for num_points / zero padding
   int rank = 0, cnt = 0;
+  int memb[8];  // opener: the (up to 8) smallest member indices, ascending = the voxel's slots (fused VFE)
   int j = (int)(unsigned int)W.head[s];
   while (j >= 0) {
     if (j < cut) {
+      if (opener && mean) {
+        int pos = min(cnt, 8);
+        if (pos < 8 || j < memb[7]) {
+          if (pos == 8) pos = 7;
+          while (pos > 0 && memb[pos - 1] > j) {
+            memb[pos] = memb[pos - 1];
+            pos--;
+          }
+          memb[pos] = j;
+        }
+      }
       cnt++;
       rank += (j < il);
     }
@@ -250,10 +264,18 @@ __global__ void __launch_bounds__(kChunk) vox_scatter_kernel(const float* __rest
     } else {
       for (int e = k * P.C; e < P.max_pts * P.C; e++) vrow[e] = 0.f;
     }
+    if (mean) {  // a2 fused: sum over the kept slots in slot order, / count (host passes mean only if max_pts <= 8)
+      const int km = min(k, 8);
+      for (int c = 0; c < P.C; c++) {
+        float sum = 0.f;
+        for (int q = 0; q < km; q++) sum += points[((size_t)start + memb[q]) * P.C + c];
+        mean[(size_t)row * P.C + c] = __fdiv_rn(sum, (float)k);
+      }
+    }
   }
 }
 
-// a2: mean over the occupied slots (zero padding makes the sum over all slots equal)
+// a2 (max_pts > 8 only): mean over the occupied slots (zero padding makes the sum over all slots equal)
 __global__ void vox_mean_kernel(const float* __restrict__ voxels, const int* __restrict__ num_points,
                                 const int* __restrict__ voxel_offsets, int B, int max_pts, int C,
                                 float* __restrict__ mean) {
@@ -545,8 +567,15 @@ extern "C" int v3d_voxelize_batch(const float* points, int total_points, int max
   VoxWs W = vox_layout(workspace, points_capacity, B);
   if (workspace_bytes < W.total) return V3D_ERR_WORKSPACE_TOO_SMALL;
   cudaStream_t st = as_stream(stream);
-  if (max_frame_points <= kVC * kVT * 4 && P.cells < 0xFFFFFFFFull) {
-    // fast path: one cluster per frame, hash table in distributed shared memory
+  // Single-kernel cluster/DSMEM variant: correct (same tests) but MEASURED SLOWER than the five-kernel
+  // global-hash path on B200 (T16: 96 us vs 53 us; ncu r01: 45 us per cluster, ~50 % long-scoreboard on
+  // remote shared-memory atomics, only 15 of the 16 clusters co-resident), so it is opt-in for experiments:
+  // V3D_VOXELIZE_CLUSTER=1.
+  static const bool use_cluster = [] {
+    const char* e = getenv("V3D_VOXELIZE_CLUSTER");
+    return e && e[0] == '1';
+  }();
+  if (use_cluster && max_frame_points <= kVC * kVT * 4 && P.cells < 0xFFFFFFFFull) {
     VClusterHdr* chdr = reinterpret_cast<VClusterHdr*>(&W.hdr->pad[0]);
     float* cmean = max_pts <= 8 ? mean : nullptr;
     const int ppt = max_frame_points <= kVC * kVT ? 1 : (max_frame_points <= kVC * kVT * 2 ? 2 : 4);
@@ -583,10 +612,12 @@ extern "C" int v3d_voxelize_batch(const float* points, int total_points, int max
   vox_count_kernel<<<grid, kChunk, 0, st>>>(frame_offsets, W);
   vox_assign_kernel<<<grid, kChunk, 0, st>>>(points, frame_offsets, P, W, coords, voxel_offsets);
   if (C == 4)
-    vox_scatter_kernel<true><<<grid, kChunk, 0, st>>>(points, frame_offsets, P, W, voxels, num_points);
+    vox_scatter_kernel<true><<<grid, kChunk, 0, st>>>(points, frame_offsets, P, W, voxels, num_points,
+                                                      max_pts <= 8 ? mean : nullptr);
   else
-    vox_scatter_kernel<false><<<grid, kChunk, 0, st>>>(points, frame_offsets, P, W, voxels, num_points);
-  if (mean) {
+    vox_scatter_kernel<false><<<grid, kChunk, 0, st>>>(points, frame_offsets, P, W, voxels, num_points,
+                                                       max_pts <= 8 ? mean : nullptr);
+  if (mean && max_pts > 8) {
     const long long rows_cap = (long long)B * max_voxels;
     const long long elems = rows_cap * C;
     const int blocks = (int)((elems + 255) / 256);

@@ -411,7 +411,7 @@ class SecondEngine:
     def _build_plan(self):
         cfg, B = self.cfg, self.B
         plan = []
-        plan.append(("voxelize+vfe", 5, lambda: self.vox.run(self.points, self.frame_off, self.max_frame_points,
+        plan.append(("voxelize+vfe", 4, lambda: self.vox.run(self.points, self.frame_off, self.max_frame_points,
                                                               self.vox_out)))
         x = self.vox_out["mean"]
         li = 0
