@@ -136,26 +136,40 @@ __device__ __forceinline__ void ldg256(const float* p, float (&v)[8]) {
                : "l"(p));
 }
 
+// per-offset usage mask -> per-group mask (GK consecutive offsets per group)
+template <int GK>
+__device__ __forceinline__ uint32_t group_mask(uint32_t m) {
+  if (GK == 1) return m;
+  uint32_t g = 0;
+#pragma unroll
+  for (int i = 0; i < 32 / GK; i++)
+    if (m & (((1u << GK) - 1u) << (i * GK))) g |= 1u << i;
+  return g;
+}
+
 constexpr int pow2_cols(int c) { return c <= 32 ? 32 : (c <= 64 ? 64 : (c <= 128 ? 128 : (c <= 256 ? 256 : 512))); }
 
 template <int CIN, int COUT>
 struct TcCfg {
-  static constexpr int kChunks = (CIN + 31) / 32;
-  static constexpr int kKSteps = CIN / 8;
-  static constexpr int kUnitsPerRow = CIN / 4;                // float4 loads per gathered row
+  // Every slot is a K = 64 GEMM step: kGK = 64/CIN consecutive kernel offsets are stacked along K (their
+  // gathered rows side by side in the A stage, their weights stacked in the B image), so small-channel layers
+  // pay the per-slot pipeline handshakes once per 64 K-elements instead of once per 16 or 32.
+  static constexpr int kGK = 64 / CIN;
+  static constexpr int kChunks = 2;
+  static constexpr int kKSteps = 8;
   // one B chunk = 2*COUT rows x 128 B: rows [0, COUT) hold W_hi^T, rows [COUT, 2*COUT) hold W_lo^T, so that
   // ONE N = 2*COUT MMA computes A_hi*[B_hi | B_lo] (the gathered operand is fetched once for both products)
   static constexpr int kBChunkBytes = 2 * COUT * 128;
-  static constexpr int kBBytes = kChunks * kBChunkBytes;      // == one prepared W[kk] image
+  static constexpr int kBBytes = kChunks * kBChunkBytes;      // == one prepared image (one offset group)
   static constexpr int kBStagesFit = (160 * 1024) / kBBytes;
   static constexpr int kBStages = kBStagesFit > 8 ? 8 : kBStagesFit;
   static constexpr int kAccBufCols = 2 * COUT;                // [A_hi*B_hi + A_lo*B_hi | A_hi*B_lo]
   static constexpr int kAccCols = 2 * kAccBufCols;            // double buffered
-  static constexpr int kAStageCols = 2 * CIN;                 // hi | lo
+  static constexpr int kAStageCols = 128;                     // 64 hi | 64 lo
   static constexpr int kAStagesFit = (512 - kAccCols) / kAStageCols;
   static constexpr int kAStages = kAStagesFit > 4 ? 4 : kAStagesFit;
   static constexpr int kTmemCols = pow2_cols(kAccCols + kAStages * kAStageCols);
-  static constexpr int kDepth = kUnitsPerRow >= 16 ? 1 : (kUnitsPerRow >= 8 ? 2 : 4);  // register sets in flight (64 floats each at CIN = 64)
+  static constexpr int kDepth = 1;                            // register sets in flight (64 floats each)
   static constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kBStages * kBBytes +
                                        sizeof(int) * kGatherGroups * kMaxKV * kTileM +
                                        1024 /*barriers + meta*/ + 2 * COUT * sizeof(float);
@@ -311,7 +325,7 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
           mbar_wait(&full_b[bs], (q / C::kBStages) & 1u);
           tc_fence_after();
           const uint64_t db0 = make_desc(b_ring + bs * (uint32_t)C::kBBytes);
-          const uint32_t a_hi = tmem_base + (uint32_t)(C::kAccCols + as * C::kAStageCols), a_lo = a_hi + CIN;
+          const uint32_t a_hi = tmem_base + (uint32_t)(C::kAccCols + as * C::kAStageCols), a_lo = a_hi + 64;
           const uint32_t d = tmem_base + (uint32_t)(a * C::kAccBufCols);
           if (elect_one()) {
 #pragma unroll
@@ -357,8 +371,9 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
         }
       }
       if (mask == 0) mask = 1u;  // must mirror the gatherers' rule
+      mask = group_mask<C::kGK>(mask);
       while (mask) {
-        const int kk = __ffs(mask) - 1;
+        const int kk = __ffs(mask) - 1;  // offset GROUP index = prepared image index
         mask &= mask - 1;
         const uint32_t bs = q % C::kBStages;
         if (lane == 0) {
@@ -374,7 +389,7 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
   } else {
     // =========================== gatherers ===========================
     constexpr int NG = kGatherWarps * 32;
-    constexpr int UPR = C::kUnitsPerRow, DEPTH = C::kDepth;
+    constexpr int DEPTH = C::kDepth;
     const int gtid = tid - 32 * (kEpiWarps + 2);
     const int grp = gtid / NG, gt = gtid % NG;
     const int my_row = 32 * (warp & 3) + lane;  // TMEM lane == tile row; a warp may only touch its lane quarter
@@ -424,6 +439,7 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
         asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(NG) : "memory");
         cur_mask = *mask_g;
         if (cur_mask == 0) cur_mask = 1u;  // cannot happen for a well-formed rule book; keeps the protocol total
+        cur_mask = group_mask<C::kGK>(cur_mask);  // slots are offset GROUPS
       }
     };
 
@@ -431,26 +447,29 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
     // a 256-bit load instruction reads 64 contiguous bytes of ONE row with the two lanes (first the even
     // lane's row, then the odd lane's), so a warp-wide LDG touches 16 lines instead of 32 (the kernel is
     // bound by L1 wavefronts otherwise); the halves are swapped back with shfl.xor before the TMEM store.
-    constexpr int NJ = CIN / 16;
+    constexpr int NJ = 4;  // 64-byte segments of the 256-byte stage row (64 K-elements)
     float v[DEPTH][NJ][2][8];  // [j][0] = loaded from the even lane's row, [j][1] = from the odd lane's row
     int it_last[DEPTH];
     uint32_t it_q[DEPTH];
     bool it_ok[DEPTH];
     auto issue = [&](int d) {
-      int kk;
-      it_ok[d] = next_item(kk, it_last[d], it_q[d]);
+      int grp_id;
+      it_ok[d] = next_item(grp_id, it_last[d], it_q[d]);
       if (!it_ok[d]) return;
-      const int src = idx_g[kk * kTileM + my_row];
-      const int src_e = __shfl_sync(0xffffffffu, src, lane & ~1);
-      const int src_o = __shfl_sync(0xffffffffu, src, lane | 1);
       const int half = lane & 1;  // which 32-byte half of every 64-byte segment this lane fetches
 #pragma unroll
       for (int j = 0; j < NJ; j++) {
+        const int off = (j * 16) / CIN;          // which offset of the group this segment belongs to
+        const int col0 = (j * 16) % CIN;         // first channel of the segment inside that offset's row
+        const int kk = grp_id * C::kGK + off;
+        const int src = kk < KV ? idx_g[kk * kTileM + my_row] : -1;
+        const int src_e = __shfl_sync(0xffffffffu, src, lane & ~1);
+        const int src_o = __shfl_sync(0xffffffffu, src, lane | 1);
 #pragma unroll
         for (int w = 0; w < 2; w++) {
           const int sr = w ? src_o : src_e;
           if (sr >= 0) {
-            ldg256(feat + (size_t)sr * CIN + 16 * j + 8 * half, v[d][j][w]);
+            ldg256(feat + (size_t)sr * CIN + col0 + 8 * half, v[d][j][w]);
           } else {
 #pragma unroll
             for (int e = 0; e < 8; e++) v[d][j][w][e] = 0.f;
@@ -508,7 +527,7 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
             lo[e] = __float_as_uint(own[e] - __uint_as_float(h));
           }
           tmem_st16(a_hi + 16u * j, hi);
-          tmem_st16(a_hi + (uint32_t)CIN + 16u * j, lo);
+          tmem_st16(a_hi + 64u + 16u * j, lo);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
@@ -541,25 +560,26 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
 // consumes: [hi | lo] x chunks x (COUT rows x 128 B), K-major, 128B-swizzled, tf32-split.
 __global__ void prepare_weights_kernel(const float* __restrict__ w, int KV, int Cin, int Cout,
                                        unsigned char* __restrict__ img) {
-  const int chunks = (Cin + 31) / 32;
-  const size_t chunk_bytes = (size_t)2 * Cout * 128, per_kk = chunks * chunk_bytes;
-  const int total = KV * Cout * chunks * 32;
+  const int gk = 64 / Cin;                      // offsets stacked along K per image
+  const int n_groups = (KV + gk - 1) / gk;
+  const size_t chunk_bytes = (size_t)2 * Cout * 128, per_group = 2 * chunk_bytes;
+  const int total = n_groups * Cout * 64;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-    const int kl = e % 32;
-    int t = e / 32;
+    const int kl = e % 64;                      // K index inside the group image
+    int t = e / 64;
     const int n = t % Cout;
-    t /= Cout;
-    const int ch = t % chunks, kk = t / chunks;
-    const int k = ch * 32 + kl;
-    const float v = k < Cin ? w[((size_t)kk * Cin + k) * Cout + n] : 0.f;
+    const int g = t / Cout;
+    const int kk = g * gk + kl / Cin, ci = kl % Cin;
+    const float v = kk < KV ? w[((size_t)kk * Cin + ci) * Cout + n] : 0.f;
     const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
     const float lo = v - hi;
+    const int ch = kl >> 5, kc = kl & 31;
     // chunk-major; inside a chunk rows [0,Cout) = hi, rows [Cout, 2*Cout) = lo (Cout is a multiple of 8, so the
     // lo rows start on an 8-row group boundary and keep the same (row & 7) swizzle phase)
     const size_t off = (size_t)ch * chunk_bytes + (size_t)(n >> 3) * 1024 + (size_t)(n & 7) * 128 +
-                       (size_t)((((kl >> 2) ^ (n & 7)) << 4) + (kl & 3) * 4);
-    *reinterpret_cast<float*>(img + (size_t)kk * per_kk + off) = hi;
-    *reinterpret_cast<float*>(img + (size_t)kk * per_kk + (size_t)Cout * 128 + off) = lo;
+                       (size_t)((((kc >> 2) ^ (n & 7)) << 4) + (kc & 3) * 4);
+    *reinterpret_cast<float*>(img + (size_t)g * per_group + off) = hi;
+    *reinterpret_cast<float*>(img + (size_t)g * per_group + (size_t)Cout * 128 + off) = lo;
   }
 }
 
@@ -591,7 +611,8 @@ using namespace v3d;
 
 extern "C" size_t v3d_sparse_conv_prepared_bytes(int kernel_volume, int Cin, int Cout) {
   if (!tc_supported(kernel_volume, Cin, Cout)) return 0;  // 0 = this shape runs on the exact-fp32 SIMT path
-  return (size_t)kernel_volume * 2 * ((Cin + 31) / 32) * Cout * 128;
+  const int gk = 64 / Cin;  // offsets per image (K = 64 per pipeline slot)
+  return (size_t)((kernel_volume + gk - 1) / gk) * 2 * (2 * Cout * 128);
 }
 
 extern "C" int v3d_sparse_conv_prepare(const float* weight, int kernel_volume, int Cin, int Cout, void* prepared,
@@ -600,7 +621,7 @@ extern "C" int v3d_sparse_conv_prepare(const float* weight, int kernel_volume, i
   const size_t need = v3d_sparse_conv_prepared_bytes(kernel_volume, Cin, Cout);
   if (need == 0) return V3D_ERR_INVALID_ARGUMENT;
   if (prepared_bytes < need) return V3D_ERR_WORKSPACE_TOO_SMALL;
-  const int total = kernel_volume * Cout * ((Cin + 31) / 32) * 32;
+  const int total = ((kernel_volume + 64 / Cin - 1) / (64 / Cin)) * Cout * 64;
   prepare_weights_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(
       weight, kernel_volume, Cin, Cout, static_cast<unsigned char*>(prepared));
   return check_launch();
