@@ -309,7 +309,7 @@ def run_b200(args):
             table.append({"op": name, "us": round(us, 2), "share": round(us / step_us, 4),
                           "alg_bytes": int(nbytes), "gbs": round(nbytes / us / 1e3, 1) if nbytes else None,
                           "tflops": round(flops / us / 1e6, 2) if flops else None})
-        mine = [r for r in table if "(" not in r["op"] and r["alg_bytes"]]
+        mine = [r for r in table if "(" not in r["op"] and r["alg_bytes"] and r["op"] != "pack_result"]
         groups = {}
         for r in mine:  # the "dominant kernel" = the v3d kernel family with the largest share of the step
             fam = "sparse_conv_fwd" if r["op"].startswith(("subm_L", "sconv_L")) else r["op"].split("_L")[0]

@@ -227,6 +227,24 @@ V3D_API int v3d_query_and_group(const float* xyz, const float* new_xyz, const fl
                                 const int* idx, int B, int C, int N, int M, int nsample, float* out,
                                 v3d_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Glue between the RPN heads and a12 for the SECOND inference path (engine-internal, replaces ~55 tiny
+ * torch launches): ProposalLayer._decode + the BEV slice + batched_nms_rotated's coordinate offsets
+ * (detector/proposal.py:47-70, core/box_encode.py:13-23, ops/iou_nms.py:121-132), and the gather of the
+ * kept boxes into packed result rows [7 box | score | frame | class | valid] (+ one row of counters).
+ *   reg_map      conv_reg output (B, n_cls*7*n_yaw, ny, nx) f32 with element strides reg_strides_host[4]
+ *   anchors      (n_cls, n_yaw, ny, nx, 7) f32 contiguous
+ *   anchor_idx   (B, n_cls, topk) int64 indices into the flattened (n_yaw, ny, nx) grid (torch.topk)
+ *   boxes (B*n_cls*topk, 7), nms_in (B*n_cls*topk, 5) outputs
+ * ------------------------------------------------------------------------------------------- */
+V3D_API int v3d_second_head_decode(const float* reg_map, const long long* reg_strides_host, const float* anchors,
+                                   const int64_t* anchor_idx, int B, int n_cls, int n_yaw, int ny, int nx,
+                                   int topk, float* boxes, float* nms_in, v3d_stream_t stream);
+V3D_API int v3d_pack_detections(const float* boxes, const float* scores, const int64_t* keep, const int* count,
+                                const float* score_thresh, int N, int n_cls, int topk,
+                                const int* const* counters_dev, int n_counters, float* result,
+                                v3d_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

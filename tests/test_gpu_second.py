@@ -205,3 +205,21 @@ def test_bev_nhwc_matches_dense_and_engine_modes_agree(cuda, no_tf32):
     for o in outs[1:]:
         assert abs(len(o[0]) - len(outs[0][0])) <= 2
         assert _match(o, outs[0]) >= 0.9 and _match(outs[0], o) >= 0.9
+
+
+def test_fused_head_kernels_match_torch_expressions(cuda, no_tf32):
+    """v3d_second_head_decode / v3d_pack_detections vs the reference's torch expression sequence."""
+    cfg = second.three_class_config()
+    model = second.init_for_benchmark(second.SecondB200(cfg), 4)
+    clouds = synth.make_batch(40, 2, 16384)
+    res = []
+    for fused in (False, True):
+        eng = second.SecondEngine(model, 2, 2 * 16384, cuda, use_graph=False, fused_head=fused).capture()
+        out = eng.infer(clouds)
+        res.append((out, eng._boxes.clone(), eng._nms_in.clone(), eng._scores.clone(), eng.h_result.clone()))
+    (o0, b0, n0, s0, r0), (o1, b1, n1, s1, r1) = res
+    assert torch.equal(s0, s1)
+    assert torch.allclose(b0, b1, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(n0, n1, rtol=1e-5, atol=1e-3)   # offsets ~1e4: fp32 spacing ~1e-3
+    assert len(o0[0]) == len(o1[0])
+    np.testing.assert_allclose(r0.numpy(), r1.numpy(), rtol=1e-5, atol=1e-4)

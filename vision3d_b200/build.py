@@ -28,6 +28,7 @@ UNITS = {
     "sparse_conv.cu": [],
     "sparse_conv_tc.cu": [],
     "dense.cu": [],
+    "head.cu": ["-fmad=false"],
     "pointops.cu": [],
 }
 

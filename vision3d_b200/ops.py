@@ -411,3 +411,35 @@ def query_and_group(xyz, new_xyz, features, idx):
                                               i.data_ptr(), B, C, N, M, ns, out.data_ptr(), _stream()),
               "v3d_query_and_group")
     return out
+
+
+# =============================================================================================
+# SECOND head glue (engine-internal)
+# =============================================================================================
+def second_head_decode(reg_out, anchors, anchor_idx, n_cls, n_yaw, topk, boxes=None, nms_in=None):
+    """reg_out: conv_reg output (B, n_cls*7*n_yaw, ny, nx), any memory format; anchor_idx (B, n_cls, topk) int64.
+    Returns boxes (N,7), nms_in (N,5) with the batched_nms_rotated group offsets applied."""
+    B, _, ny, nx = reg_out.shape
+    N = B * n_cls * topk
+    dev = reg_out.device
+    if boxes is None:
+        boxes = torch.empty((N, 7), dtype=_F32, device=dev)
+    if nms_in is None:
+        nms_in = torch.empty((N, 5), dtype=_F32, device=dev)
+    strides = (ctypes.c_longlong * 4)(*[int(v) for v in reg_out.stride()])
+    with torch.cuda.device(dev):
+        check(_lib.load().v3d_second_head_decode(reg_out.data_ptr(), strides, anchors.data_ptr(),
+                                                 anchor_idx.data_ptr(), B, int(n_cls), int(n_yaw), ny, nx,
+                                                 int(topk), boxes.data_ptr(), nms_in.data_ptr(), _stream()),
+              "v3d_second_head_decode")
+    return boxes, nms_in
+
+
+def pack_detections(boxes, scores, keep, count, thr, n_cls, topk, counters_ptrs, n_counters, result):
+    N = boxes.shape[0]
+    with torch.cuda.device(boxes.device):
+        check(_lib.load().v3d_pack_detections(boxes.data_ptr(), scores.data_ptr(), keep.data_ptr(), count.data_ptr(),
+                                              thr.data_ptr(), N, int(n_cls), int(topk),
+                                              counters_ptrs.data_ptr() if counters_ptrs is not None else None,
+                                              int(n_counters), result.data_ptr(), _stream()), "v3d_pack_detections")
+    return result

@@ -298,7 +298,8 @@ def _fold_bn(bn):
 
 class SecondEngine:
     def __init__(self, model: SecondB200, batch_size: int, points_capacity: int, device, level_caps=None,
-                 use_graph=True, cap_policy=0, frame_points_capacity=None, tensor_cores=True, rpn_mode="fused"):
+                 use_graph=True, cap_policy=0, frame_points_capacity=None, tensor_cores=True, rpn_mode="fused",
+                 fused_head=True):
         cfg = model.cfg
         self.cfg, self.B, self.P = cfg, int(batch_size), int(points_capacity)
         self.dev = torch.device(device)
@@ -378,6 +379,11 @@ class SecondEngine:
         self.result = torch.zeros((self.N + 1, 11), dtype=torch.float32, device=dev)
         self.h_result = torch.zeros((self.N + 1, 11), dtype=torch.float32).pin_memory()
         self.graph = None
+        # ---- head glue: one decode kernel + one pack kernel instead of ~55 tiny torch launches
+        self.fused_head = bool(fused_head)
+        self._boxes_buf = torch.empty((self.N, 7), dtype=torch.float32, device=dev)
+        self._nms_buf = torch.empty((self.N, 5), dtype=torch.float32, device=dev)
+        self._counter_ptrs = torch.tensor([t.data_ptr() for t in self.n_rows], dtype=torch.int64, device=dev)
         # ---- RPN (stays cuDNN): "module" = the nn.Sequential as is; "fused" = eval BatchNorm2d folded into
         # the conv weights + cudnn fused conv-bias-ReLU (7 launches instead of 21, no separate BN/ReLU passes
         # over the 288 MB activations); "fused_nhwc" = same in channels_last.
@@ -463,9 +469,9 @@ class SecondEngine:
                 x, self.indices[4], self.n_rows[4], self.caps[4], B, self.shapes[4], self.dense_out,
                 self.dense_ws))))
         plan.append(("rpn(cudnn)", 0, self._rpn))
-        plan.append(("head_topk_decode(torch)", 0, self._head))
+        plan.append(("heads+topk(torch)+decode", 1 if self.fused_head else 0, self._head))
         plan.append(("nms_rotated", 3, self._nms))
-        plan.append(("pack_result(torch)", 0, self._pack))
+        plan.append(("pack_result", 1 if self.fused_head else 0, self._pack))
         self.plan = plan
         self.kernel_launches = sum(p[1] for p in plan)
 
@@ -484,15 +490,31 @@ class SecondEngine:
 
     def _head(self):
         cfg = self.cfg
-        boxes, scores = self.model.head.candidates(self._fmap, self.anchors)
-        self._scores, self._boxes = scores.reshape(-1), boxes.reshape(-1, cfg.BOX_DOF)
-        self._nms_in = group_offsets(self._boxes.index_select(1, self.bev_cols), self.g_idx)
+        if not self.fused_head:  # the reference's torch expression sequence (proposal.py:61-78)
+            boxes, scores = self.model.head.candidates(self._fmap, self.anchors)
+            self._scores, self._boxes = scores.reshape(-1), boxes.reshape(-1, cfg.BOX_DOF)
+            self._nms_in = group_offsets(self._boxes.index_select(1, self.bev_cols), self.g_idx)
+            return
+        # 1x1 heads + sigmoid + top-k stay torch/cuDNN; gather + decode + BEV + group offsets = one kernel
+        head = self.model.head
+        B, n_cls = self.B, cfg.NUM_CLASSES
+        cls = head.conv_cls(self._fmap).reshape(B, n_cls, -1)  # channel = class * n_yaw + yaw
+        reg = head.conv_reg(self._fmap)
+        scores, a_idx = cls.sigmoid().topk(cfg.TOPK, -1)
+        self._scores = scores.reshape(-1)
+        ops.second_head_decode(reg, self.anchors, a_idx.contiguous(), n_cls, cfg.NUM_YAW, cfg.TOPK,
+                               self._boxes_buf, self._nms_buf)
+        self._boxes, self._nms_in = self._boxes_buf, self._nms_buf
 
     def _nms(self):
         self.keep.zero_()
         ops.nms_rotated_padded(self._nms_in, self._scores, self.cfg.NMS_THRESH, self.nms_ws, self.keep, self.count)
 
     def _pack(self):
+        if self.fused_head:
+            ops.pack_detections(self._boxes, self._scores, self.keep, self.count, self.thr, self.cfg.NUM_CLASSES,
+                                self.cfg.TOPK, self._counter_ptrs, 5, self.result)
+            return
         k = self.keep
         ks, kc = self._scores[k], self.c_idx[k]
         valid = (ks > self.thr[kc]) & (self.row_ids < self.count)
