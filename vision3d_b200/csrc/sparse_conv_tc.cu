@@ -2,40 +2,53 @@
 // (kind::tf32, 3xTF32 split for fp32-grade accuracy), accumulators AND the gathered A operand in TMEM,
 // folded BN + ReLU epilogue.
 //
-// One persistent CTA per SM, warp specialised (448 threads):
-//   warps 0-3  epilogue   : tcgen05.ld the 128 x COUT fp32 accumulator (lane = output row), apply
-//                           scale/shift/ReLU, store each output row once
-//   warp  4    MMA issuer : warp-uniform loop, one elected lane issues per pipeline slot 2*(CIN/8)
-//                           tcgen05.mma with A from TMEM and B from shared memory, K=8:
-//                           A_hi*[B_hi|B_lo] (M=128, N=2*COUT) and A_lo*B_hi (N=COUT); tcgen05.commit frees the A stage, the B
-//                           stage and publishes the accumulator through mbarriers
-//   warp  5    weight TMA : finds the kernel offsets each tile uses and streams the pre-swizzled,
-//                           pre-split W[kk] images (hi+lo) with cp.async.bulk (1-D TMA) into a deep
-//                           shared-memory ring, running up to kBStages slots ahead of the MMAs
-//   warps 6-13 gatherers  : two independent groups of 4 warps, slot q belongs to group q % 2; thread =
-//                           output row. A thread gathers its neighbour's feature row with 128-bit
-//                           loads issued up to kDepth slots AHEAD into registers, splits every value
-//                           into tf32 hi / lo parts and tcgen05.st's them into the TMEM A stage.
-// Why A goes through TMEM: with both operands in shared memory a 3xTF32 N=64 tile is bound by the
-// 128 B/clk shared-memory port (each K=8 step re-reads 4 KB of A three times: measured 2900 clk per
-// slot against 830 clk of tensor math). TMEM-resident A leaves only the 2 KB B reads on that port.
+// One persistent CTA per SM, warp specialised (576 threads):
+//   warps 0-3   epilogue   : tcgen05.ld the 128 x COUT fp32 accumulator (lane = output row), apply
+//                            scale/shift/ReLU, store each output row once
+//   warp  4     MMA issuer : warp-uniform loop, one elected lane issues per pipeline slot 2*8 tcgen05.mma
+//                            with A from TMEM and B from shared memory, K=8: A_hi*[B_hi|B_lo] (M=128,
+//                            N=2*COUT) and A_lo*B_hi (N=COUT); tcgen05.commit frees the A stage, the B
+//                            stage and publishes the accumulator through mbarriers
+//   warp  5     weight TMA : finds the kernel offsets each tile uses and streams the pre-swizzled,
+//                            pre-split W images (hi+lo) with cp.async.bulk (1-D TMA) into a shared-memory
+//                            ring, running up to kBStages slots ahead of the MMAs
+//   warps 6-9   fetchers   : stage the tile's rule rows in shared memory (the next tile's are prefetched
+//                            into registers), then for every slot issue 16-byte cp.async copies of the
+//                            gathered neighbour rows (zero-fill for missing neighbours) into a ring of raw
+//                            fp32 tiles; completion is tracked by mbarriers (cp.async.mbarrier.arrive), so
+//                            the global-load latency of kSStages slots is in flight without holding a
+//                            single register
+//   warps 10-17 converters : two groups of 4 warps, slot q belongs to group q % 2; thread = output row. A
+//                            thread reads its 256-byte row from the ring (conflict-free: 272-byte pitch),
+//                            splits every value into tf32 hi / lo parts and tcgen05.st's them into the
+//                            TMEM A stage.
+// Why A goes through TMEM: with both operands in shared memory every K=8 step re-reads 4 KB of A three
+// times; TMEM-resident A leaves only the B reads on the shared-memory port.
+// Why fetch and convert are separate roles: with register-staged gathers (LDG -> split -> TMEM in one
+// thread) the gather warps were issue/latency bound at ~3000 clk per slot (measured: tensor pipe 50 %
+// active, gather warps never waiting on a barrier).
 // Output rows are written exactly once (no atomics, deterministic). Arithmetic: every product is
 // exact in fp32 (11-bit x 11-bit mantissas); dropping only a_lo*b_lo bounds the relative error of a
 // product by ~2^-21, far inside the 1e-4 the contract allows.
 //
-// B operand layout (K-major, SWIZZLE_128B, fp32 elements): a "chunk" is COUT rows x 128 bytes
-// (32 K-elements); 8-row groups are 1024 B apart (SBO); the 16-byte unit u of row r lives at unit
-// u ^ (r & 7). CIN = 64 uses two chunks, CIN = 16 uses half of one.
-// TMEM columns: [0, 2*COUT) two accumulator buffers; then kAStages x (CIN hi | CIN lo) A stages.
+// B operand layout (K-major, SWIZZLE_128B, fp32 elements): a "chunk" is 2*COUT rows x 128 bytes
+// (32 K-elements; rows [0,COUT) = W_hi^T, rows [COUT,2*COUT) = W_lo^T); 8-row groups are 1024 B apart
+// (SBO); the 16-byte unit u of row r lives at unit u ^ (r & 7). A slot is always K = 64 (two chunks):
+// 64/CIN consecutive kernel offsets are stacked along K.
+// TMEM columns: [0, 4*COUT) two accumulator buffers; then kAStages x (64 hi | 64 lo) A stages.
 #include "common.cuh"
 
 namespace v3d {
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kEpiWarps = 4, kGatherWarps = 4, kGatherGroups = 2;
-constexpr int kThreads = 32 * (kEpiWarps + 2 + kGatherWarps * kGatherGroups);  // 448
-constexpr int kMaxKV = 32;
+constexpr int kEpiWarps = 4, kFetchWarps = 4, kConvWarps = 4, kConvGroups = 2;
+constexpr int kWarpMma = kEpiWarps, kWarpB = kEpiWarps + 1, kWarpFetch0 = kEpiWarps + 2;
+constexpr int kWarpConv0 = kWarpFetch0 + kFetchWarps;
+constexpr int kThreads = 32 * (kWarpConv0 + kConvWarps * kConvGroups);  // 576
+constexpr int kMaxKV = 27;
+constexpr int kRowPitch = 256 + 16;              // bytes between rows of a raw A tile (bank-conflict-free)
+constexpr int kStageBytes = kTileM * kRowPitch;  // one raw fp32 A tile: 128 rows x 64 K-elements
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -61,7 +74,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!ok);
 }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -72,15 +84,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+// 16-byte asynchronous copy global -> shared; src_bytes = 0 writes zeros (missing neighbour)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+// the mbarrier receives one arrival once all cp.async issued so far by this thread have landed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -101,6 +113,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// A operand from TMEM, B from shared memory
 __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
                                              uint32_t accumulate) {
   asm volatile(
@@ -130,12 +143,6 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
       : "memory");
 }
 
-__device__ __forceinline__ void ldg256(const float* p, float (&v)[8]) {
-  asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
-               : "l"(p));
-}
-
 // per-offset usage mask -> per-group mask (GK consecutive offsets per group)
 template <int GK>
 __device__ __forceinline__ uint32_t group_mask(uint32_t m) {
@@ -160,25 +167,25 @@ struct TcCfg {
   // one B chunk = 2*COUT rows x 128 B: rows [0, COUT) hold W_hi^T, rows [COUT, 2*COUT) hold W_lo^T, so that
   // ONE N = 2*COUT MMA computes A_hi*[B_hi | B_lo] (the gathered operand is fetched once for both products)
   static constexpr int kBChunkBytes = 2 * COUT * 128;
-  static constexpr int kBBytes = kChunks * kBChunkBytes;      // == one prepared image (one offset group)
-  static constexpr int kBStagesFit = (160 * 1024) / kBBytes;
-  static constexpr int kBStages = kBStagesFit > 8 ? 8 : kBStagesFit;
-  static constexpr int kAccBufCols = 2 * COUT;                // [A_hi*B_hi + A_lo*B_hi | A_hi*B_lo]
-  static constexpr int kAccCols = 2 * kAccBufCols;            // double buffered
-  static constexpr int kAStageCols = 128;                     // 64 hi | 64 lo
+  static constexpr int kBBytes = kChunks * kBChunkBytes;  // == one prepared image (one offset group)
+  static constexpr int kBStages = COUT == 64 ? 3 : 4;
+  static constexpr int kSStages = COUT == 64 ? 3 : 4;     // raw A tiles in flight (fetch -> convert ring)
+  static constexpr int kAccBufCols = 2 * COUT;            // [A_hi*B_hi + A_lo*B_hi | A_hi*B_lo]
+  static constexpr int kAccCols = 2 * kAccBufCols;        // double buffered
+  static constexpr int kAStageCols = 128;                 // 64 hi | 64 lo
   static constexpr int kAStagesFit = (512 - kAccCols) / kAStageCols;
   static constexpr int kAStages = kAStagesFit > 4 ? 4 : kAStagesFit;
   static constexpr int kTmemCols = pow2_cols(kAccCols + kAStages * kAStageCols);
-  static constexpr int kDepth = 1;                            // register sets in flight (64 floats each)
   static constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kBStages * kBBytes +
-                                       sizeof(int) * kGatherGroups * kMaxKV * kTileM +
+                                       (size_t)kSStages * kStageBytes + sizeof(int) * kMaxKV * kTileM +
                                        1024 /*barriers + meta*/ + 2 * COUT * sizeof(float);
-  static_assert(kAStages >= 2 && kBStages >= 2, "pipeline needs two stages");
+  static_assert(kAStages >= 2 && kBStages >= 2 && kSStages >= 2, "pipeline needs two stages");
+  static_assert(kSmemBytes <= 232448, "shared memory budget (227 KB per CTA)");
 };
 
 struct SlotMeta {
   int last;  // 1 = last slot of its output tile
-  int end;   // 1 = all tiles done
+  int end;   // != 0: all tiles done (1 = forward the termination to the MMA warp, 2 = just stop)
 };
 
 template <int CIN, int COUT>
@@ -189,19 +196,25 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
                       float* __restrict__ out) {
   using C = TcCfg<CIN, COUT>;
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  unsigned char* bring = base;                                                        // kBStages x (B_hi B_lo)
-  int* idx_tile = reinterpret_cast<int*>(base + (size_t)C::kBStages * C::kBBytes);    // [group][KV][128]
-  unsigned char* tail = reinterpret_cast<unsigned char*>(idx_tile + kGatherGroups * kMaxKV * kTileM);
+  // round up to 1024 B (SWIZZLE_128B atoms) by OFFSETTING the __shared__ array: casting through an integer
+  // would make every later access a generic LD/ST instead of LDS/STS
+  unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* bring = base;                                         // kBStages x [B_hi | B_lo] images
+  unsigned char* sring = bring + (size_t)C::kBStages * C::kBBytes;     // kSStages x raw fp32 A tiles
+  int* idx_tile = reinterpret_cast<int*>(sring + (size_t)C::kSStages * kStageBytes);  // [KV][128]
+  unsigned char* tail = reinterpret_cast<unsigned char*>(idx_tile + kMaxKV * kTileM);
   uint64_t* full_a = reinterpret_cast<uint64_t*>(tail);  // [4]
   uint64_t* empty_a = full_a + 4;                        // [4]
-  uint64_t* full_b = empty_a + 4;                        // [8]
-  uint64_t* empty_b = full_b + 8;                        // [8]
-  uint64_t* acc_full = empty_b + 8;                      // [2]
+  uint64_t* full_b = empty_a + 4;                        // [4]
+  uint64_t* empty_b = full_b + 4;                        // [4]
+  uint64_t* acc_full = empty_b + 4;                      // [2]
   uint64_t* acc_empty = acc_full + 2;                    // [2]
-  SlotMeta* meta = reinterpret_cast<SlotMeta*>(acc_empty + 2);  // [4]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(meta + 4);
-  uint32_t* tile_mask = tmem_slot + 1;  // [kGatherGroups]
+  uint64_t* sfull = acc_empty + 2;                       // [4]
+  uint64_t* sempty = sfull + 4;                          // [4]
+  SlotMeta* meta = reinterpret_cast<SlotMeta*>(sempty + 4);  // [4]  converter -> MMA issuer (per A stage)
+  SlotMeta* smeta = meta + 4;                                // [4]  fetcher -> converter (per raw stage)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smeta + 4);
+  uint32_t* fmask = tmem_slot + 1;  // [2] offsets used by the tile being staged (parity double buffer)
   float* s_scale = reinterpret_cast<float*>(tail + 1024);
   float* s_shift = s_scale + COUT;
 
@@ -211,7 +224,7 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
 
   if (tid == 0) {
     for (int s = 0; s < C::kAStages; s++) {
-      mbar_init(&full_a[s], kGatherWarps * 32);  // the one group that owns the slot
+      mbar_init(&full_a[s], kConvWarps * 32);  // the one converter group that owns the slot
       mbar_init(&empty_a[s], 1);
     }
     for (int s = 0; s < C::kBStages; s++) {
@@ -222,6 +235,11 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
       mbar_init(&acc_full[a], 1);
       mbar_init(&acc_empty[a], kEpiWarps * 32);
     }
+    for (int s = 0; s < C::kSStages; s++) {
+      mbar_init(&sfull[s], kFetchWarps * 32 + 1);  // every fetch thread's cp.async group + the meta writer
+      mbar_init(&sempty[s], kConvWarps * 32);
+    }
+    fmask[0] = fmask[1] = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int c = tid; c < COUT; c += kThreads) {
@@ -294,61 +312,59 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
         }
       }
     }
-  } else if (warp == kEpiWarps) {
+  } else if (warp == kWarpMma) {
     // =========================== MMA issuer ===========================
     // The WHOLE warp walks the slot sequence with warp-uniform control flow and only the tcgen05
     // instructions are predicated on one elected lane: operands then live in uniform registers. (With a
     // single divergent thread every UTCHMMA needed ELECT + R2UR moves: ~380 SASS instructions and ~2500
     // clk of issue time per slot, three times the 768 clk the tensor pipe needs.)
-    {
-      constexpr uint32_t idesc_wide = make_idesc(kTileM, 2 * COUT), idesc_hi = make_idesc(kTileM, COUT);
-      const uint32_t b_ring = smem_u32(bring);
-      uint32_t q = 0;
-      int it = 0;
-      bool done = false;
-      while (!done) {
-        const int a = it & 1;
-        uint32_t accum = 0u;
-        bool tile_open = false;
-        while (true) {
-          const uint32_t as = q % C::kAStages, bs = q % C::kBStages;
-          mbar_wait(&full_a[as], (q / C::kAStages) & 1u);
-          const int m_last = meta[as].last, m_end = meta[as].end;
-          if (m_end) {
-            done = true;
-            break;
-          }
-          if (!tile_open) {  // first slot of a tile: the accumulator buffer must have been drained
-            mbar_wait(&acc_empty[a], ((it >> 1) & 1) ^ 1);
-            tile_open = true;
-          }
-          mbar_wait(&full_b[bs], (q / C::kBStages) & 1u);
-          tc_fence_after();
-          const uint64_t db0 = make_desc(b_ring + bs * (uint32_t)C::kBBytes);
-          const uint32_t a_hi = tmem_base + (uint32_t)(C::kAccCols + as * C::kAStageCols), a_lo = a_hi + 64;
-          const uint32_t d = tmem_base + (uint32_t)(a * C::kAccBufCols);
-          if (elect_one()) {
-#pragma unroll
-            for (int ks = 0; ks < C::kKSteps; ks++) {
-              // descriptor start address advances in 16-byte units (low 14 bits of the descriptor)
-              const uint64_t db = db0 + (uint64_t)(((ks >> 2) * C::kBChunkBytes + (ks & 3) * 32) >> 4);
-              umma_tf32_ts(d, a_hi + 8u * ks, db, idesc_wide, accum);  // A_hi * [B_hi | B_lo], N = 2*COUT
-              umma_tf32_ts(d, a_lo + 8u * ks, db, idesc_hi, 1u);       // A_lo * B_hi into the first COUT columns
-              accum = 1u;
-            }
-            umma_commit(&empty_a[as]);  // stages reusable once these MMAs have read them
-            umma_commit(&empty_b[bs]);
-            if (m_last) umma_commit(&acc_full[a]);
-          }
-          accum = 1u;
-          __syncwarp();
-          q++;
-          if (m_last) break;
+    constexpr uint32_t idesc_wide = make_idesc(kTileM, 2 * COUT), idesc_hi = make_idesc(kTileM, COUT);
+    const uint32_t b_ring = smem_u32(bring);
+    uint32_t q = 0;
+    int it = 0;
+    bool done = false;
+    while (!done) {
+      const int a = it & 1;
+      uint32_t accum = 0u;
+      bool tile_open = false;
+      while (true) {
+        const uint32_t as = q % C::kAStages, bs = q % C::kBStages;
+        mbar_wait(&full_a[as], (q / C::kAStages) & 1u);
+        const int m_last = meta[as].last, m_end = meta[as].end;
+        if (m_end) {
+          done = true;
+          break;
         }
-        it++;
+        if (!tile_open) {  // first slot of a tile: the accumulator buffer must have been drained
+          mbar_wait(&acc_empty[a], ((it >> 1) & 1) ^ 1);
+          tile_open = true;
+        }
+        mbar_wait(&full_b[bs], (q / C::kBStages) & 1u);
+        tc_fence_after();
+        const uint64_t db0 = make_desc(b_ring + bs * (uint32_t)C::kBBytes);
+        const uint32_t a_hi = tmem_base + (uint32_t)(C::kAccCols + as * C::kAStageCols), a_lo = a_hi + 64;
+        const uint32_t d = tmem_base + (uint32_t)(a * C::kAccBufCols);
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < C::kKSteps; ks++) {
+            // descriptor start address advances in 16-byte units (low 14 bits of the descriptor)
+            const uint64_t db = db0 + (uint64_t)(((ks >> 2) * C::kBChunkBytes + (ks & 3) * 32) >> 4);
+            umma_tf32_ts(d, a_hi + 8u * ks, db, idesc_wide, accum);  // A_hi * [B_hi | B_lo], N = 2*COUT
+            umma_tf32_ts(d, a_lo + 8u * ks, db, idesc_hi, 1u);       // A_lo * B_hi into the first COUT columns
+            accum = 1u;
+          }
+          umma_commit(&empty_a[as]);  // stages reusable once these MMAs have read them
+          umma_commit(&empty_b[bs]);
+          if (m_last) umma_commit(&acc_full[a]);
+        }
+        accum = 1u;
+        __syncwarp();
+        q++;
+        if (m_last) break;
       }
+      it++;
     }
-  } else if (warp == kEpiWarps + 1) {
+  } else if (warp == kWarpB) {
     // =========================== weight loader (1-D TMA), whole warp ===========================
     uint32_t q = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -370,7 +386,7 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
           if (__any_sync(0xffffffffu, any)) mask |= 1u << (k0 + u);
         }
       }
-      if (mask == 0) mask = 1u;  // must mirror the gatherers' rule
+      if (mask == 0) mask = 1u;  // must mirror the fetchers' rule
       mask = group_mask<C::kGK>(mask);
       while (mask) {
         const int kk = __ffs(mask) - 1;  // offset GROUP index = prepared image index
@@ -386,164 +402,135 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
       }
       __syncwarp();
     }
-  } else {
-    // =========================== gatherers ===========================
-    constexpr int NG = kGatherWarps * 32;
-    constexpr int DEPTH = C::kDepth;
-    const int gtid = tid - 32 * (kEpiWarps + 2);
-    const int grp = gtid / NG, gt = gtid % NG;
-    const int my_row = 32 * (warp & 3) + lane;  // TMEM lane == tile row; a warp may only touch its lane quarter
-    int* idx_g = idx_tile + grp * kMaxKV * kTileM;
-    uint32_t* mask_g = tile_mask + grp;
+  } else if (warp < kWarpConv0) {
+    // =========================== fetchers ===========================
+    constexpr int NF = kFetchWarps * 32;
+    const int fw = warp - kWarpFetch0, gt = fw * 32 + lane;
+    // copy geometry: 16 consecutive lanes cover one 256-byte stage row (two rows per warp instruction)
+    const int unit = lane & 15, rsub = lane >> 4;
+    const int off = (unit * 4) / CIN;   // which offset of the slot's group this 16-byte unit belongs to
+    const int col = (unit * 4) % CIN;   // first channel of the unit inside that offset's feature row
+    const uint32_t dst_lane = smem_u32(sring) + (uint32_t)((fw * 2 + rsub) * kRowPitch + unit * 16);
 
-    // Cursor over the CTA's sequence of non-empty (tile, offset) slots; every group walks the whole
-    // sequence (so slot numbers agree) and keeps the slots with q % kGatherGroups == grp.
-    int cur_tile = (int)blockIdx.x - (int)gridDim.x;
-    uint32_t cur_mask = 0, q_next = 0;
-    auto next_item = [&](int& kk, int& last, uint32_t& q) -> bool {
-      while (true) {
-        while (cur_mask) {
-          kk = __ffs(cur_mask) - 1;
-          cur_mask &= cur_mask - 1;
-          q = q_next++;
-          if ((int)(q % kGatherGroups) == grp) {
-            last = (cur_mask == 0);
-            return true;
-          }
-        }
-        cur_tile += gridDim.x;
-        if (cur_tile >= n_tiles) return false;
-        // stage this tile's rule rows (group-private copy) and find the offsets it uses
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(NG) : "memory");  // loads that used idx_g are issued
-        if (gt == 0) *mask_g = 0u;
-        const int o = cur_tile * kTileM + gt;
-        {
-          const int* src = nbr + o;
-#pragma unroll 9
-          for (int k2 = 0; k2 < KV; k2++) {
-            const int v = o < n_out ? __ldg(src + (size_t)k2 * nbr_stride) : -1;
-            idx_g[k2 * kTileM + gt] = v;
-          }
-        }
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(NG) : "memory");
-        {
-          const int w = gt >> 5;
-          uint32_t mine = 0;
-          for (int k2 = w; k2 < KV; k2 += kGatherWarps) {
-            const int* row = idx_g + k2 * kTileM;
-            const bool any = (row[lane] >= 0) | (row[lane + 32] >= 0) | (row[lane + 64] >= 0) | (row[lane + 96] >= 0);
-            if (__any_sync(0xffffffffu, any)) mine |= 1u << k2;
-          }
-          if (lane == 0 && mine) atomicOr(mask_g, mine);
-        }
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(NG) : "memory");
-        cur_mask = *mask_g;
-        if (cur_mask == 0) cur_mask = 1u;  // cannot happen for a well-formed rule book; keeps the protocol total
-        cur_mask = group_mask<C::kGK>(cur_mask);  // slots are offset GROUPS
-      }
+    int pre[kMaxKV];  // rule rows of the NEXT tile (row = gt), in flight while the current tile is fetched
+    auto prefetch = [&](int tile) {
+      const int o = tile * kTileM + gt;
+      const bool ok = tile < n_tiles && o < n_out;
+#pragma unroll
+      for (int k = 0; k < kMaxKV; k++) pre[k] = (ok && k < KV) ? __ldg(nbr + (size_t)k * nbr_stride + o) : -1;
     };
-
-    // Register image of one gathered row: CIN/16 pairs of 32-byte chunks. Lanes 2i and 2i+1 cooperate:
-    // a 256-bit load instruction reads 64 contiguous bytes of ONE row with the two lanes (first the even
-    // lane's row, then the odd lane's), so a warp-wide LDG touches 16 lines instead of 32 (the kernel is
-    // bound by L1 wavefronts otherwise); the halves are swapped back with shfl.xor before the TMEM store.
-    constexpr int NJ = 4;  // 64-byte segments of the 256-byte stage row (64 K-elements)
-    float v[DEPTH][NJ][2][8];  // [j][0] = loaded from the even lane's row, [j][1] = from the odd lane's row
-    int it_last[DEPTH];
-    uint32_t it_q[DEPTH];
-    bool it_ok[DEPTH];
-    auto issue = [&](int d) {
-      int grp_id;
-      it_ok[d] = next_item(grp_id, it_last[d], it_q[d]);
-      if (!it_ok[d]) return;
-      const int half = lane & 1;  // which 32-byte half of every 64-byte segment this lane fetches
+    prefetch(blockIdx.x);
+    uint32_t q = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+      asm volatile("bar.sync 1, %0;" ::"n"(NF) : "memory");  // all copies that read idx_tile are issued
+      if (gt == 0) fmask[(it + 1) & 1] = 0u;
+      uint32_t mine = 0;
 #pragma unroll
-      for (int j = 0; j < NJ; j++) {
-        const int off = (j * 16) / CIN;          // which offset of the group this segment belongs to
-        const int col0 = (j * 16) % CIN;         // first channel of the segment inside that offset's row
-        const int kk = grp_id * C::kGK + off;
-        const int src = kk < KV ? idx_g[kk * kTileM + my_row] : -1;
-        const int src_e = __shfl_sync(0xffffffffu, src, lane & ~1);
-        const int src_o = __shfl_sync(0xffffffffu, src, lane | 1);
-#pragma unroll
-        for (int w = 0; w < 2; w++) {
-          const int sr = w ? src_o : src_e;
-          if (sr >= 0) {
-            ldg256(feat + (size_t)sr * CIN + col0 + 8 * half, v[d][j][w]);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; e++) v[d][j][w][e] = 0.f;
-          }
-        }
+      for (int k = 0; k < kMaxKV; k++) {
+        if (k < KV) idx_tile[k * kTileM + gt] = pre[k];
+        if (__any_sync(0xffffffffu, pre[k] >= 0)) mine |= 1u << k;
       }
-    };
+      if (lane == 0 && mine) atomicOr(&fmask[it & 1], mine);
+      asm volatile("bar.sync 1, %0;" ::"n"(NF) : "memory");
+      uint32_t mask = fmask[it & 1];
+      if (mask == 0) mask = 1u;  // cannot happen for a well-formed rule book; keeps the protocol total
+      mask = group_mask<C::kGK>(mask);
+      prefetch(tile + gridDim.x);
+      while (mask) {
+        const int g = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const uint32_t s = q % C::kSStages;
+        mbar_wait(&sempty[s], ((q / C::kSStages) & 1u) ^ 1u);
+        const int kk = g * C::kGK + off;
+        const bool kv_ok = kk < KV;  // the last group of a layer may be padded with non-existent offsets
+        const int* idx_row = idx_tile + (kv_ok ? kk : 0) * kTileM + fw * 2 + rsub;
+        const uint32_t dst = dst_lane + s * (uint32_t)kStageBytes;
+        int src[16];
 #pragma unroll
-    for (int d = 0; d < DEPTH; d++) it_ok[d] = false;
+        for (int i = 0; i < 16; i++) src[i] = idx_row[8 * i];  // rows 8 i + 2 fw + rsub
 #pragma unroll
-    for (int d = 0; d < DEPTH; d++) {
-      bool prev_ok = true;
-#pragma unroll
-      for (int e = 0; e < d; e++) prev_ok = prev_ok && it_ok[e];
-      if (prev_ok) issue(d);
-    }
-    const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
-    bool running = true;
-    while (running) {
-#pragma unroll
-      for (int d = 0; d < DEPTH; d++) {
-        if (!running) break;
-        if (!it_ok[d]) {
-          running = false;
-          break;
+        for (int i = 0; i < 16; i++) {
+          const bool ok = kv_ok && src[i] >= 0;
+          const float* p = feat + (size_t)(ok ? src[i] : 0) * CIN + col;
+          cp_async16(dst + (uint32_t)(8 * i * kRowPitch), p, ok ? 16u : 0u);
         }
-        const uint32_t q = it_q[d];
-        const uint32_t as = q % C::kAStages;
-        mbar_wait(&empty_a[as], ((q / C::kAStages) & 1u) ^ 1u);
-        tc_fence_after();
+        cp_async_arrive_noinc(&sfull[s]);
         if (gt == 0) {
-          meta[as].last = it_last[d];
-          meta[as].end = 0;
+          smeta[s].last = (mask == 0);
+          smeta[s].end = 0;
+          mbar_arrive(&sfull[s]);  // release: publishes the meta write
         }
-        const uint32_t a_hi = tmem_base + lane_base + (uint32_t)(C::kAccCols + as * C::kAStageCols);
-#pragma unroll
-        for (int j = 0; j < NJ; j++) {
-          // swap halves inside the lane pair: the even lane gives away what it fetched of the odd lane's
-          // row ([j][1]) and receives the upper half of its own row; the odd lane the other way round
-          float own[16];
-          const int half = lane & 1;
-#pragma unroll
-          for (int e = 0; e < 8; e++) {
-            const float give = half ? v[d][j][0][e] : v[d][j][1][e];
-            const float got = __shfl_xor_sync(0xffffffffu, give, 1);
-            const float keep = half ? v[d][j][1][e] : v[d][j][0][e];
-            own[e] = half ? got : keep;       // columns 16j + 0..7  of my row
-            own[8 + e] = half ? keep : got;   // columns 16j + 8..15 of my row
-          }
-          uint32_t hi[16], lo[16];
-#pragma unroll
-          for (int e = 0; e < 16; e++) {
-            const uint32_t h = __float_as_uint(own[e]) & 0xFFFFE000u;
-            hi[e] = h;
-            lo[e] = __float_as_uint(own[e] - __uint_as_float(h));
-          }
-          tmem_st16(a_hi + 16u * j, hi);
-          tmem_st16(a_hi + 64u + 16u * j, lo);
-        }
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        tc_fence_before();
-        mbar_arrive(&full_a[as]);  // release also orders the meta write of gt == 0
-        issue(d);  // refill this register set: loads fly while the other sets / the other group are processed
+        q++;
       }
     }
-    // termination slot: sequence number = total slot count, posted by the group that owns it
-    if ((int)(q_next % kGatherGroups) == grp) {
-      const uint32_t as = q_next % C::kAStages;
-      mbar_wait(&empty_a[as], ((q_next / C::kAStages) & 1u) ^ 1u);
+    // two termination slots, one per converter group
+    for (int t = 0; t < kConvGroups; t++) {
+      const uint32_t s = q % C::kSStages;
+      mbar_wait(&sempty[s], ((q / C::kSStages) & 1u) ^ 1u);
+      cp_async_arrive_noinc(&sfull[s]);
       if (gt == 0) {
-        meta[as].last = 1;
-        meta[as].end = 1;
+        smeta[s].last = 1;
+        smeta[s].end = 1 + t;
+        mbar_arrive(&sfull[s]);
       }
-      mbar_arrive(&full_a[as]);
+      q++;
+    }
+  } else {
+    // =========================== converters ===========================
+    const int cw = warp - kWarpConv0;
+    const int grp = cw / kConvWarps;
+    const bool leader = (cw % kConvWarps) == 0 && lane == 0;
+    const int my_row = 32 * (warp & 3) + lane;  // TMEM lane == tile row; a warp may only touch its lane quarter
+    const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
+    for (uint32_t q = grp;; q += kConvGroups) {
+      const uint32_t s = q % C::kSStages, as = q % C::kAStages;
+      mbar_wait(&sfull[s], (q / C::kSStages) & 1u);
+      const int m_last = smeta[s].last, m_end = smeta[s].end;
+      if (m_end) {
+        if (m_end == 1) {  // this group owns the slot number the MMA warp will look at next
+          mbar_wait(&empty_a[as], ((q / C::kAStages) & 1u) ^ 1u);
+          if (leader) {
+            meta[as].last = 1;
+            meta[as].end = 1;
+          }
+          mbar_arrive(&full_a[as]);
+        }
+        break;
+      }
+      mbar_wait(&empty_a[as], ((q / C::kAStages) & 1u) ^ 1u);
+      tc_fence_after();
+      if (leader) {
+        meta[as].last = m_last;
+        meta[as].end = 0;
+      }
+      const float4* rowp = reinterpret_cast<const float4*>(sring + (size_t)s * kStageBytes + (size_t)my_row * kRowPitch);
+      const uint32_t a_hi = tmem_base + lane_base + (uint32_t)(C::kAccCols + as * C::kAStageCols);
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        float own[16];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const float4 x = rowp[4 * j + u];
+          own[4 * u + 0] = x.x;
+          own[4 * u + 1] = x.y;
+          own[4 * u + 2] = x.z;
+          own[4 * u + 3] = x.w;
+        }
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+          const uint32_t h = __float_as_uint(own[e]) & 0xFFFFE000u;
+          hi[e] = h;
+          lo[e] = __float_as_uint(own[e] - __uint_as_float(h));
+        }
+        tmem_st16(a_hi + 16u * j, hi);
+        tmem_st16(a_hi + 64u + 16u * j, lo);
+      }
+      mbar_arrive(&sempty[s]);  // the row has been consumed (the TMEM stores depend on every load)
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      mbar_arrive(&full_a[as]);  // release also orders the leader's meta write
     }
   }
 
@@ -556,8 +543,8 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
   }
 }
 
-// One-time weight preparation: (KV, Cin, Cout) fp32 -> per kk the exact shared-memory image the kernel
-// consumes: [hi | lo] x chunks x (COUT rows x 128 B), K-major, 128B-swizzled, tf32-split.
+// One-time weight preparation: (KV, Cin, Cout) fp32 -> per offset group the exact shared-memory image the
+// kernel consumes: chunks x ([hi rows | lo rows] x 128 B), K-major, 128B-swizzled, tf32-split.
 __global__ void prepare_weights_kernel(const float* __restrict__ w, int KV, int Cin, int Cout,
                                        unsigned char* __restrict__ img) {
   const int gk = 64 / Cin;                      // offsets stacked along K per image
