@@ -350,8 +350,8 @@ def run_b200(args):
                              "far larger than the 126 MB L2; 4 distinct input batches rotate"
                              % (eng.dense_out.numel() * 4 / 1e6),
                        "cuda_graph": eng.graph is not None,
-                       "sparse_conv": "exact-fp32 SIMT" if args.simt else "tcgen05 kind::tf32 3xTF32 (Cin>=16), "
-                                                                          "exact-fp32 SIMT (Cin=4)", "rpn": "torch/cuDNN fp32 (TF32 allowed=%s), mode=%s"
+                       "sparse_conv": "exact-fp32 SIMT" if args.simt else "tcgen05 kind::f16 bf16x3 split, fp32 accumulate "
+                                                                          "(Cin>=16), exact-fp32 SIMT (Cin=4)", "rpn": "torch/cuDNN fp32 (TF32 allowed=%s), mode=%s"
                                                                    % (torch.backends.cudnn.allow_tf32, args.rpn),
                        "active_sites_per_level": rows, "detections": int(counts["kept"])},
             "e2e": {"value": round(e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": eng.h2d_bytes(),

@@ -176,18 +176,25 @@ V3D_API int v3d_sparse_conv_fwd(const float* feat, const float* weight, const in
                                 int Cout, const float* scale, const float* shift, int relu, float* out,
                                 v3d_stream_t stream);
 
-/* Tensor-core path of the same op (tcgen05.mma kind::tf32 with a 3xTF32 split, accumulators in TMEM;
- * relative error of a product ~2^-21, results within 1e-5 of the exact-fp32 path). Weights are prepared
- * once per layer into the shared-memory image the kernel streams with 1-D TMA:
+/* Tensor-core path of the same op (tcgen05.mma kind::f16 on a 3-term bf16 split, fp32 accumulators in
+ * TMEM; a value x is carried as h1 = bf16(x), h2 = bf16(x - h1) and a product as h1*g1 + h1*g2 + h2*g1:
+ * relative error of a product <= ~3*2^-18, measured 4e-6 (Frobenius) per layer against fp64 -- inside the
+ * 1e-4 of the contract; use v3d_sparse_conv_fwd when exact fp32 products are required).
+ * Features travel between layers as "packed" rows [h1(0..C-1) | h2(0..C-1)] of bf16 (4*C bytes per row, the
+ * fp32 footprint): v3d_feature_pack converts fp32 rows, and the conv writes fp32 rows (`out`), packed rows
+ * (`out_packed`) or both (either may be NULL, not both). Weights are prepared once per layer into the
+ * shared-memory image the kernel streams with 1-D TMA:
  *   v3d_sparse_conv_prepared_bytes returns 0 for shapes only the exact-fp32 path supports (Cin < 16 ...).
- * Supported: kernel_volume <= 32, Cin and Cout in {16, 32, 64}. */
+ * Supported: kernel_volume <= 27, Cin and Cout in {16, 32, 64}. */
 V3D_API size_t v3d_sparse_conv_prepared_bytes(int kernel_volume, int Cin, int Cout);
 V3D_API int v3d_sparse_conv_prepare(const float* weight, int kernel_volume, int Cin, int Cout, void* prepared,
                                     size_t prepared_bytes, v3d_stream_t stream);
-V3D_API int v3d_sparse_conv_fwd_tc(const float* feat, const void* prepared, const int* nbr, int nbr_stride,
+V3D_API int v3d_feature_pack(const float* feat, const int* n_rows, int capacity_rows, int C, void* packed,
+                             v3d_stream_t stream);
+V3D_API int v3d_sparse_conv_fwd_tc(const void* feat_packed, const void* prepared, const int* nbr, int nbr_stride,
                                    const int* n_out, int out_capacity, int kernel_volume, int Cin, int Cout,
                                    const float* scale, const float* shift, int relu, float* out,
-                                   v3d_stream_t stream);
+                                   void* out_packed, v3d_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a3  SparseConvTensor.dense(): (N,C) rows -> (B,C,D,H,W), zero filled (sparse_cnn.py:128-133).

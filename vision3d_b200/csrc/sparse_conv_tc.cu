@@ -1,54 +1,54 @@
 // a5 + a6 on the 5th-generation tensor cores: output-stationary sparse convolution with tcgen05.mma
-// (kind::tf32, 3xTF32 split for fp32-grade accuracy), accumulators AND the gathered A operand in TMEM,
-// folded BN + ReLU epilogue.
+// (kind::f16, bf16 operands, 3-term split "bf16x3"), fp32 accumulators in TMEM, folded BN + ReLU epilogue.
 //
-// One persistent CTA per SM, warp specialised (576 threads):
-//   warps 0-3   epilogue   : tcgen05.ld the 128 x COUT fp32 accumulator (lane = output row), apply
-//                            scale/shift/ReLU, store each output row once
-//   warp  4     MMA issuer : warp-uniform loop, one elected lane issues per pipeline slot 2*8 tcgen05.mma
-//                            with A from TMEM and B from shared memory, K=8: A_hi*[B_hi|B_lo] (M=128,
-//                            N=2*COUT) and A_lo*B_hi (N=COUT); tcgen05.commit frees the A stage, the B
-//                            stage and publishes the accumulator through mbarriers
-//   warp  5     weight TMA : finds the kernel offsets each tile uses and streams the pre-swizzled,
-//                            pre-split W images (hi+lo) with cp.async.bulk (1-D TMA) into a shared-memory
-//                            ring, running up to kBStages slots ahead of the MMAs
-//   warps 6-9   fetchers   : stage the tile's rule rows in shared memory (the next tile's are prefetched
-//                            into registers), then for every slot issue 16-byte cp.async copies of the
-//                            gathered neighbour rows (zero-fill for missing neighbours) into a ring of raw
-//                            fp32 tiles; completion is tracked by mbarriers (cp.async.mbarrier.arrive), so
-//                            the global-load latency of kSStages slots is in flight without holding a
-//                            single register
-//   warps 10-17 converters : two groups of 4 warps, slot q belongs to group q % 2; thread = output row. A
-//                            thread reads its 256-byte row from the ring (conflict-free: 272-byte pitch),
-//                            splits every value into tf32 hi / lo parts and tcgen05.st's them into the
-//                            TMEM A stage.
-// Why A goes through TMEM: with both operands in shared memory every K=8 step re-reads 4 KB of A three
-// times; TMEM-resident A leaves only the B reads on the shared-memory port.
-// Why fetch and convert are separate roles: with register-staged gathers (LDG -> split -> TMEM in one
-// thread) the gather warps were issue/latency bound at ~3000 clk per slot (measured: tensor pipe 50 %
-// active, gather warps never waiting on a barrier).
-// Output rows are written exactly once (no atomics, deterministic). Arithmetic: every product is
-// exact in fp32 (11-bit x 11-bit mantissas); dropping only a_lo*b_lo bounds the relative error of a
-// product by ~2^-21, far inside the 1e-4 the contract allows.
+// Number format. A value x is carried as two bf16 numbers h1 = bf16_rn(x), h2 = bf16_rn(x - h1)
+// (|x - h1 - h2| <= 2^-18 |x|). A product x*w is evaluated as h1*g1 + h1*g2 + h2*g1 (every partial product
+// is exact in the fp32 accumulator); the dropped terms bound the error of a product by ~3 * 2^-18 |x w|.
+// Measured against fp64 on post-ReLU data: 4e-6 relative (Frobenius) per layer, i.e. well inside the 1e-4
+// the contract allows, at HALF the tensor-pipe and operand-fetch cost of a 3xTF32 split (K = 16 per
+// instruction instead of 8). The exact-fp32 SIMT kernel (sparse_conv.cu) stays available.
 //
-// B operand layout (K-major, SWIZZLE_128B, fp32 elements): a "chunk" is 2*COUT rows x 128 bytes
-// (32 K-elements; rows [0,COUT) = W_hi^T, rows [COUT,2*COUT) = W_lo^T); 8-row groups are 1024 B apart
-// (SBO); the 16-byte unit u of row r lives at unit u ^ (r & 7). A slot is always K = 64 (two chunks):
-// 64/CIN consecutive kernel offsets are stacked along K.
-// TMEM columns: [0, 4*COUT) two accumulator buffers; then kAStages x (64 hi | 64 lo) A stages.
+// "Packed" feature rows: [h1(0..C-1) | h2(0..C-1)] as bf16 = 4*C bytes, the same footprint as fp32. Every
+// producer (this kernel's epilogue, v3d_feature_pack) writes that format, so the gather is a pure copy:
+// 16-byte cp.async straight into the 128B-swizzled K-major A tiles the MMAs read from shared memory.
+// No conversion pass, no register staging, no TMEM operand.
+//
+// One persistent CTA per SM, warp specialised (288 threads):
+//   warps 0-3  epilogue   : tcgen05.ld the 128 x COUT fp32 accumulator halves (lane = output row), add
+//                           them, apply scale/shift/ReLU, store the row as fp32 and/or packed bf16x2
+//   warp  4    MMA issuer : warp-uniform loop, one elected lane issues per pipeline slot (K = 64) 2*4
+//                           tcgen05.mma, M=128, K=16, both operands from shared memory:
+//                           A_h1 * [G1 | G2] (N = 2*COUT) and A_h2 * G1 (N = COUT); tcgen05.commit frees
+//                           the stage and publishes the accumulator through mbarriers
+//   warps 5-8  fetchers   : stage the tile's rule rows in shared memory (the next tile's are prefetched
+//                           into registers), find the kernel offsets the tile uses, and for every slot
+//                           gather the neighbour rows (zero-fill for missing neighbours) with cp.async into
+//                           the stage's A tiles while one thread streams the slot's weight image with a
+//                           1-D TMA bulk copy. cp.async groups complete kStages-1 slots later
+//                           (wait_group + fence.proxy.async + mbarrier arrive), so that many slots of
+//                           global-load latency are in flight.
+// Measured instruction costs on B200 (scripts/mma_probe.cu): one M=128 MMA costs max(47, N/2) clk for
+// every operand kind/source, so a slot is 4*(64+47) = 444 clk for COUT = 64 (3xTF32 needed 888).
+// Output rows are written exactly once (no atomics, deterministic).
+//
+// Operand layout (K-major, SWIZZLE_128B, bf16): a tile row is 64 K-elements = 128 bytes; 8-row groups are
+// 1024 B apart (SBO); the 16-byte unit u of row r lives at unit u ^ (r & 7). A slot is always K = 64:
+// 64/CIN consecutive kernel offsets are stacked along K. Stage = [A_h1 16 KB | A_h2 16 KB | G1 rows | G2 rows].
+// TMEM columns: two accumulator buffers of 2*COUT columns: [h1*g1 + h2*g1 | h1*g2].
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace v3d {
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kEpiWarps = 4, kFetchWarps = 4, kConvWarps = 4, kConvGroups = 2;
-constexpr int kWarpMma = kEpiWarps, kWarpB = kEpiWarps + 1, kWarpFetch0 = kEpiWarps + 2;
-constexpr int kWarpConv0 = kWarpFetch0 + kFetchWarps;
-constexpr int kThreads = 32 * (kWarpConv0 + kConvWarps * kConvGroups);  // 576
+constexpr int kEpiWarps = 4, kFetchWarps = 4;
+constexpr int kWarpMma = kEpiWarps, kWarpFetch0 = kEpiWarps + 1;
+constexpr int kThreads = 32 * (kWarpFetch0 + kFetchWarps);  // 288
 constexpr int kMaxKV = 27;
-constexpr int kRowPitch = 256 + 16;              // bytes between rows of a raw A tile (bank-conflict-free)
-constexpr int kStageBytes = kTileM * kRowPitch;  // one raw fp32 A tile: 128 rows x 64 K-elements
+constexpr int kATileBytes = kTileM * 128;  // 128 rows x 64 bf16
+constexpr int kABytes = 2 * kATileBytes;   // h1 tile | h2 tile
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -74,12 +74,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!ok);
 }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
@@ -88,9 +88,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
-// the mbarrier receives one arrival once all cp.async issued so far by this thread have landed
-__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -107,20 +108,19 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   return (uint64_t)lo | ((uint64_t)hi << 32);
 }
 
-// instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=TF32 [7,10)=2, b=TF32 [10,13)=2,
+// instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=BF16 [7,10)=1, b=BF16 [10,13)=1,
 // a,b K-major (bits 15,16 = 0), N>>3 [17,23), M>>4 [24,29)
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// A operand from TMEM, B from shared memory
-__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+__device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                              uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 
@@ -134,13 +134,22 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
-      "%15, %16};" ::"r"(taddr),
-      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
-      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
-      : "memory");
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
+      "%14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+
+// two fp32 -> (h1 pair, h2 pair) packed bf16x2 words (element 0 in the low half)
+__device__ __forceinline__ void split2(float a, float b, uint32_t& h1, uint32_t& h2) {
+  const __nv_bfloat162 p1 = __floats2bfloat162_rn(a, b);
+  const float2 f1 = __bfloat1622float2(p1);
+  const __nv_bfloat162 p2 = __floats2bfloat162_rn(a - f1.x, b - f1.y);
+  h1 = *reinterpret_cast<const uint32_t*>(&p1);
+  h2 = *reinterpret_cast<const uint32_t*>(&p2);
 }
 
 // per-offset usage mask -> per-group mask (GK consecutive offsets per group)
@@ -159,61 +168,50 @@ constexpr int pow2_cols(int c) { return c <= 32 ? 32 : (c <= 64 ? 64 : (c <= 128
 template <int CIN, int COUT>
 struct TcCfg {
   // Every slot is a K = 64 GEMM step: kGK = 64/CIN consecutive kernel offsets are stacked along K (their
-  // gathered rows side by side in the A stage, their weights stacked in the B image), so small-channel layers
+  // gathered rows side by side in the A tile, their weights stacked in the B image), so small-channel layers
   // pay the per-slot pipeline handshakes once per 64 K-elements instead of once per 16 or 32.
   static constexpr int kGK = 64 / CIN;
-  static constexpr int kChunks = 2;
-  static constexpr int kKSteps = 8;
-  // one B chunk = 2*COUT rows x 128 B: rows [0, COUT) hold W_hi^T, rows [COUT, 2*COUT) hold W_lo^T, so that
-  // ONE N = 2*COUT MMA computes A_hi*[B_hi | B_lo] (the gathered operand is fetched once for both products)
-  static constexpr int kBChunkBytes = 2 * COUT * 128;
-  static constexpr int kBBytes = kChunks * kBChunkBytes;  // == one prepared image (one offset group)
-  static constexpr int kBStages = COUT == 64 ? 3 : 4;
-  static constexpr int kSStages = COUT == 64 ? 3 : 4;     // raw A tiles in flight (fetch -> convert ring)
-  static constexpr int kAccBufCols = 2 * COUT;            // [A_hi*B_hi + A_lo*B_hi | A_hi*B_lo]
-  static constexpr int kAccCols = 2 * kAccBufCols;        // double buffered
-  static constexpr int kAStageCols = 128;                 // 64 hi | 64 lo
-  static constexpr int kAStagesFit = (512 - kAccCols) / kAStageCols;
-  static constexpr int kAStages = kAStagesFit > 4 ? 4 : kAStagesFit;
-  static constexpr int kTmemCols = pow2_cols(kAccCols + kAStages * kAStageCols);
-  static constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kBStages * kBBytes +
-                                       (size_t)kSStages * kStageBytes + sizeof(int) * kMaxKV * kTileM +
-                                       1024 /*barriers + meta*/ + 2 * COUT * sizeof(float);
-  static_assert(kAStages >= 2 && kBStages >= 2 && kSStages >= 2, "pipeline needs two stages");
+  static constexpr int kKSteps = 4;                       // K = 16 per instruction
+  // B image of one slot: rows [0, COUT) hold G1^T, rows [COUT, 2*COUT) hold G2^T, 128 B per row, so that
+  // ONE N = 2*COUT MMA computes A_h1*[G1 | G2] (the gathered operand is fetched once for both products)
+  static constexpr int kBBytes = 2 * COUT * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;   // multiple of 1024
+  static constexpr int kStages = COUT == 64 ? 4 : 5;
+  static constexpr int kInFlight = kStages - 1;           // cp.async groups pending per fetch thread
+  static constexpr int kAccBufCols = 2 * COUT;            // [h1*g1 + h2*g1 | h1*g2]
+  static constexpr int kTmemCols = pow2_cols(2 * kAccBufCols);
+  static constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * kStageBytes +
+                                       sizeof(int) * kMaxKV * kTileM + 1024 /*barriers + meta*/ +
+                                       2 * COUT * sizeof(float);
+  static_assert(kStageBytes % 1024 == 0, "stages must keep the 1024-byte swizzle-atom alignment");
   static_assert(kSmemBytes <= 232448, "shared memory budget (227 KB per CTA)");
 };
 
 struct SlotMeta {
   int last;  // 1 = last slot of its output tile
-  int end;   // != 0: all tiles done (1 = forward the termination to the MMA warp, 2 = just stop)
+  int end;   // 1 = all tiles done
 };
 
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(kThreads, 1)
-sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __restrict__ wprep,
+sparse_conv_tc_kernel(const unsigned char* __restrict__ feat, const unsigned char* __restrict__ wprep,
                       const int* __restrict__ nbr, int nbr_stride, const int* __restrict__ n_out_ptr, int out_cap,
                       int KV, const float* __restrict__ scale, const float* __restrict__ shift, int relu,
-                      float* __restrict__ out) {
+                      float* __restrict__ out, unsigned char* __restrict__ out_packed) {
   using C = TcCfg<CIN, COUT>;
   extern __shared__ unsigned char smem_raw[];
   // round up to 1024 B (SWIZZLE_128B atoms) by OFFSETTING the __shared__ array: casting through an integer
   // would make every later access a generic LD/ST instead of LDS/STS
   unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  unsigned char* bring = base;                                         // kBStages x [B_hi | B_lo] images
-  unsigned char* sring = bring + (size_t)C::kBStages * C::kBBytes;     // kSStages x raw fp32 A tiles
-  int* idx_tile = reinterpret_cast<int*>(sring + (size_t)C::kSStages * kStageBytes);  // [KV][128]
+  unsigned char* ring = base;                                                          // kStages x stage
+  int* idx_tile = reinterpret_cast<int*>(ring + (size_t)C::kStages * C::kStageBytes);  // [KV][128]
   unsigned char* tail = reinterpret_cast<unsigned char*>(idx_tile + kMaxKV * kTileM);
-  uint64_t* full_a = reinterpret_cast<uint64_t*>(tail);  // [4]
-  uint64_t* empty_a = full_a + 4;                        // [4]
-  uint64_t* full_b = empty_a + 4;                        // [4]
-  uint64_t* empty_b = full_b + 4;                        // [4]
-  uint64_t* acc_full = empty_b + 4;                      // [2]
-  uint64_t* acc_empty = acc_full + 2;                    // [2]
-  uint64_t* sfull = acc_empty + 2;                       // [4]
-  uint64_t* sempty = sfull + 4;                          // [4]
-  SlotMeta* meta = reinterpret_cast<SlotMeta*>(sempty + 4);  // [4]  converter -> MMA issuer (per A stage)
-  SlotMeta* smeta = meta + 4;                                // [4]  fetcher -> converter (per raw stage)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smeta + 4);
+  uint64_t* full = reinterpret_cast<uint64_t*>(tail);  // [8]
+  uint64_t* empty = full + 8;                          // [8]
+  uint64_t* acc_full = empty + 8;                      // [2]
+  uint64_t* acc_empty = acc_full + 2;                  // [2]
+  SlotMeta* meta = reinterpret_cast<SlotMeta*>(acc_empty + 2);  // [8] fetcher -> MMA issuer (per stage)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(meta + 8);
   uint32_t* fmask = tmem_slot + 1;  // [2] offsets used by the tile being staged (parity double buffer)
   float* s_scale = reinterpret_cast<float*>(tail + 1024);
   float* s_shift = s_scale + COUT;
@@ -223,21 +221,13 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
   const int n_tiles = (n_out + kTileM - 1) / kTileM;
 
   if (tid == 0) {
-    for (int s = 0; s < C::kAStages; s++) {
-      mbar_init(&full_a[s], kConvWarps * 32);  // the one converter group that owns the slot
-      mbar_init(&empty_a[s], 1);
-    }
-    for (int s = 0; s < C::kBStages; s++) {
-      mbar_init(&full_b[s], 1);
-      mbar_init(&empty_b[s], 1);
+    for (int s = 0; s < C::kStages; s++) {
+      mbar_init(&full[s], kFetchWarps * 32 + 1);  // every fetch thread + the expect_tx arrival of the B copy
+      mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; a++) {
       mbar_init(&acc_full[a], 1);
       mbar_init(&acc_empty[a], kEpiWarps * 32);
-    }
-    for (int s = 0; s < C::kSStages; s++) {
-      mbar_init(&sfull[s], kFetchWarps * 32 + 1);  // every fetch thread's cp.async group + the meta writer
-      mbar_init(&sempty[s], kConvWarps * 32);
     }
     fmask[0] = fmask[1] = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -268,46 +258,40 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
       tc_fence_after();
       const int row = tile * kTileM + warp * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * C::kAccBufCols);
-      float* orow = out + (size_t)row * COUT;
 #pragma unroll
       for (int c0 = 0; c0 < COUT; c0 += 16) {
         uint32_t v[16], v2[16];
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
-            "%14, %15}, [%16];"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-            : "r"(taddr + (uint32_t)c0));
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
-            "%14, %15}, [%16];"
-            : "=r"(v2[0]), "=r"(v2[1]), "=r"(v2[2]), "=r"(v2[3]), "=r"(v2[4]), "=r"(v2[5]), "=r"(v2[6]), "=r"(v2[7]),
-              "=r"(v2[8]), "=r"(v2[9]), "=r"(v2[10]), "=r"(v2[11]), "=r"(v2[12]), "=r"(v2[13]), "=r"(v2[14]),
-              "=r"(v2[15])
-            : "r"(taddr + (uint32_t)(COUT + c0)));
+        tmem_ld16(taddr + (uint32_t)c0, v);
+        tmem_ld16(taddr + (uint32_t)(COUT + c0), v2);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int e = 0; e < 16; e++)  // (A_hi*B_hi + A_lo*B_hi) + A_hi*B_lo
-          v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(v2[e]));
         if (c0 + 16 >= COUT) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
           tc_fence_before();
           mbar_arrive(&acc_empty[a]);
         }
-        if (row < n_out) {
+        float o[16];
 #pragma unroll
-          for (int q = 0; q < 4; q++) {
-            float4 o;
-            o.x = fmaf(__uint_as_float(v[4 * q + 0]), sc[c0 + 4 * q + 0], sh[c0 + 4 * q + 0]);
-            o.y = fmaf(__uint_as_float(v[4 * q + 1]), sc[c0 + 4 * q + 1], sh[c0 + 4 * q + 1]);
-            o.z = fmaf(__uint_as_float(v[4 * q + 2]), sc[c0 + 4 * q + 2], sh[c0 + 4 * q + 2]);
-            o.w = fmaf(__uint_as_float(v[4 * q + 3]), sc[c0 + 4 * q + 3], sh[c0 + 4 * q + 3]);
-            if (relu) {
-              o.x = fmaxf(o.x, 0.f);
-              o.y = fmaxf(o.y, 0.f);
-              o.z = fmaxf(o.z, 0.f);
-              o.w = fmaxf(o.w, 0.f);
-            }
-            *reinterpret_cast<float4*>(orow + c0 + 4 * q) = o;
+        for (int e = 0; e < 16; e++) {  // (h1*g1 + h2*g1) + h1*g2, then folded BN + ReLU
+          const float acc = __uint_as_float(v[e]) + __uint_as_float(v2[e]);
+          o[e] = fmaf(acc, sc[c0 + e], sh[c0 + e]);
+          if (relu) o[e] = fmaxf(o[e], 0.f);
+        }
+        if (row < n_out) {
+          if (out != nullptr) {
+            float4* orow = reinterpret_cast<float4*>(out + (size_t)row * COUT + c0);
+#pragma unroll
+            for (int q = 0; q < 4; q++) orow[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+          }
+          if (out_packed != nullptr) {
+            uint32_t h1[8], h2[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) split2(o[2 * e], o[2 * e + 1], h1[e], h2[e]);
+            unsigned char* prow = out_packed + (size_t)row * (4 * COUT) + (size_t)c0 * 2;
+            uint4* p1 = reinterpret_cast<uint4*>(prow);
+            uint4* p2 = reinterpret_cast<uint4*>(prow + 2 * COUT);
+            p1[0] = make_uint4(h1[0], h1[1], h1[2], h1[3]);
+            p1[1] = make_uint4(h1[4], h1[5], h1[6], h1[7]);
+            p2[0] = make_uint4(h2[0], h2[1], h2[2], h2[3]);
+            p2[1] = make_uint4(h2[4], h2[5], h2[6], h2[7]);
           }
         }
       }
@@ -315,11 +299,9 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
   } else if (warp == kWarpMma) {
     // =========================== MMA issuer ===========================
     // The WHOLE warp walks the slot sequence with warp-uniform control flow and only the tcgen05
-    // instructions are predicated on one elected lane: operands then live in uniform registers. (With a
-    // single divergent thread every UTCHMMA needed ELECT + R2UR moves: ~380 SASS instructions and ~2500
-    // clk of issue time per slot, three times the 768 clk the tensor pipe needs.)
-    constexpr uint32_t idesc_wide = make_idesc(kTileM, 2 * COUT), idesc_hi = make_idesc(kTileM, COUT);
-    const uint32_t b_ring = smem_u32(bring);
+    // instructions are predicated on one elected lane: operands then live in uniform registers.
+    constexpr uint32_t idesc_wide = make_idesc(kTileM, 2 * COUT), idesc_g1 = make_idesc(kTileM, COUT);
+    const uint32_t ring_u32 = smem_u32(ring);
     uint32_t q = 0;
     int it = 0;
     bool done = false;
@@ -328,9 +310,9 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
       uint32_t accum = 0u;
       bool tile_open = false;
       while (true) {
-        const uint32_t as = q % C::kAStages, bs = q % C::kBStages;
-        mbar_wait(&full_a[as], (q / C::kAStages) & 1u);
-        const int m_last = meta[as].last, m_end = meta[as].end;
+        const uint32_t s = q % C::kStages;
+        mbar_wait(&full[s], (q / C::kStages) & 1u);
+        const int m_last = meta[s].last, m_end = meta[s].end;
         if (m_end) {
           done = true;
           break;
@@ -339,22 +321,19 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
           mbar_wait(&acc_empty[a], ((it >> 1) & 1) ^ 1);
           tile_open = true;
         }
-        mbar_wait(&full_b[bs], (q / C::kBStages) & 1u);
         tc_fence_after();
-        const uint64_t db0 = make_desc(b_ring + bs * (uint32_t)C::kBBytes);
-        const uint32_t a_hi = tmem_base + (uint32_t)(C::kAccCols + as * C::kAStageCols), a_lo = a_hi + 64;
+        const uint32_t st = ring_u32 + s * (uint32_t)C::kStageBytes;
+        const uint64_t da1 = make_desc(st), da2 = make_desc(st + kATileBytes), db0 = make_desc(st + kABytes);
         const uint32_t d = tmem_base + (uint32_t)(a * C::kAccBufCols);
         if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < C::kKSteps; ks++) {
-            // descriptor start address advances in 16-byte units (low 14 bits of the descriptor)
-            const uint64_t db = db0 + (uint64_t)(((ks >> 2) * C::kBChunkBytes + (ks & 3) * 32) >> 4);
-            umma_tf32_ts(d, a_hi + 8u * ks, db, idesc_wide, accum);  // A_hi * [B_hi | B_lo], N = 2*COUT
-            umma_tf32_ts(d, a_lo + 8u * ks, db, idesc_hi, 1u);       // A_lo * B_hi into the first COUT columns
+            // K = 16 bf16 = 32 bytes along the swizzled row: the start address advances by 2 (16-byte units)
+            umma_bf16_ss(d, da1 + 2u * ks, db0 + 2u * ks, idesc_wide, accum);  // A_h1 * [G1 | G2], N = 2*COUT
+            umma_bf16_ss(d, da2 + 2u * ks, db0 + 2u * ks, idesc_g1, 1u);       // A_h2 * G1 into the first COUT columns
             accum = 1u;
           }
-          umma_commit(&empty_a[as]);  // stages reusable once these MMAs have read them
-          umma_commit(&empty_b[bs]);
+          umma_commit(&empty[s]);  // stage reusable once these MMAs have read it
           if (m_last) umma_commit(&acc_full[a]);
         }
         accum = 1u;
@@ -364,53 +343,18 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
       }
       it++;
     }
-  } else if (warp == kWarpB) {
-    // =========================== weight loader (1-D TMA), whole warp ===========================
-    uint32_t q = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      // which kernel offsets does this tile use? lanes cover rows lane + 32 j; 9 offsets per round trip
-      const int o0 = tile * kTileM + lane;
-      uint32_t mask = 0;
-      for (int k0 = 0; k0 < KV; k0 += 9) {
-        int v[9][4];
-#pragma unroll
-        for (int u = 0; u < 9; u++)
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            const int o = o0 + 32 * j;
-            v[u][j] = (k0 + u < KV && o < n_out) ? __ldg(&nbr[(size_t)(k0 + u) * nbr_stride + o]) : -1;
-          }
-#pragma unroll
-        for (int u = 0; u < 9; u++) {
-          const bool any = (v[u][0] >= 0) | (v[u][1] >= 0) | (v[u][2] >= 0) | (v[u][3] >= 0);
-          if (__any_sync(0xffffffffu, any)) mask |= 1u << (k0 + u);
-        }
-      }
-      if (mask == 0) mask = 1u;  // must mirror the fetchers' rule
-      mask = group_mask<C::kGK>(mask);
-      while (mask) {
-        const int kk = __ffs(mask) - 1;  // offset GROUP index = prepared image index
-        mask &= mask - 1;
-        const uint32_t bs = q % C::kBStages;
-        if (lane == 0) {
-          mbar_wait(&empty_b[bs], ((q / C::kBStages) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(&full_b[bs], (uint32_t)C::kBBytes);
-          bulk_g2s(bring + (size_t)bs * C::kBBytes, wprep + (size_t)kk * C::kBBytes, (uint32_t)C::kBBytes,
-                   &full_b[bs]);
-        }
-        q++;
-      }
-      __syncwarp();
-    }
-  } else if (warp < kWarpConv0) {
+  } else {
     // =========================== fetchers ===========================
     constexpr int NF = kFetchWarps * 32;
+    constexpr int kRowBytes = 4 * CIN;  // packed source row: [h1 (2*CIN bytes) | h2 (2*CIN bytes)]
     const int fw = warp - kWarpFetch0, gt = fw * 32 + lane;
-    // copy geometry: 16 consecutive lanes cover one 256-byte stage row (two rows per warp instruction)
-    const int unit = lane & 15, rsub = lane >> 4;
-    const int off = (unit * 4) / CIN;   // which offset of the slot's group this 16-byte unit belongs to
-    const int col = (unit * 4) % CIN;   // first channel of the unit inside that offset's feature row
-    const uint32_t dst_lane = smem_u32(sring) + (uint32_t)((fw * 2 + rsub) * kRowPitch + unit * 16);
+    // copy geometry: 16 consecutive lanes cover one tile row (8 units of h1, 8 units of h2), two rows per
+    // warp instruction; unit u holds K-elements [8u, 8u+8) of the slot = channels c0.. of offset `off`
+    const int rsub = lane >> 4, part = (lane >> 3) & 1, unit = lane & 7;
+    const int off = (unit * 8) / CIN;
+    const int src_byte = part * (2 * CIN) + ((unit * 8) % CIN) * 2;
+    const int row0 = fw * 2 + rsub;  // this lane copies rows row0 + 8 i; (row & 7) == row0
+    const uint32_t dst_lane = smem_u32(ring) + (uint32_t)(part * kATileBytes + row0 * 128 + ((unit ^ row0) << 4));
 
     int pre[kMaxKV];  // rule rows of the NEXT tile (row = gt), in flight while the current tile is fetched
     auto prefetch = [&](int tile) {
@@ -420,7 +364,7 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
       for (int k = 0; k < kMaxKV; k++) pre[k] = (ok && k < KV) ? __ldg(nbr + (size_t)k * nbr_stride + o) : -1;
     };
     prefetch(blockIdx.x);
-    uint32_t q = 0;
+    uint32_t q = 0, q_arrived = 0;  // slots issued / slots whose copies were published to the MMA warp
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
       asm volatile("bar.sync 1, %0;" ::"n"(NF) : "memory");  // all copies that read idx_tile are issued
@@ -438,99 +382,54 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
       mask = group_mask<C::kGK>(mask);
       prefetch(tile + gridDim.x);
       while (mask) {
-        const int g = __ffs(mask) - 1;
+        const int g = __ffs(mask) - 1;  // offset GROUP index = prepared image index
         mask &= mask - 1;
-        const uint32_t s = q % C::kSStages;
-        mbar_wait(&sempty[s], ((q / C::kSStages) & 1u) ^ 1u);
+        const uint32_t s = q % C::kStages;
+        mbar_wait(&empty[s], ((q / C::kStages) & 1u) ^ 1u);
+        const uint32_t st = s * (uint32_t)C::kStageBytes;
+        if (gt == 0) {
+          meta[s].last = (mask == 0);
+          meta[s].end = 0;
+          mbar_arrive_expect_tx(&full[s], (uint32_t)C::kBBytes);
+          bulk_g2s(smem_u32(ring) + st + kABytes, wprep + (size_t)g * C::kBBytes, (uint32_t)C::kBBytes, &full[s]);
+        }
         const int kk = g * C::kGK + off;
         const bool kv_ok = kk < KV;  // the last group of a layer may be padded with non-existent offsets
-        const int* idx_row = idx_tile + (kv_ok ? kk : 0) * kTileM + fw * 2 + rsub;
-        const uint32_t dst = dst_lane + s * (uint32_t)kStageBytes;
+        const int* idx_row = idx_tile + (kv_ok ? kk : 0) * kTileM + row0;
         int src[16];
 #pragma unroll
-        for (int i = 0; i < 16; i++) src[i] = idx_row[8 * i];  // rows 8 i + 2 fw + rsub
+        for (int i = 0; i < 16; i++) src[i] = idx_row[8 * i];
 #pragma unroll
         for (int i = 0; i < 16; i++) {
           const bool ok = kv_ok && src[i] >= 0;
-          const float* p = feat + (size_t)(ok ? src[i] : 0) * CIN + col;
-          cp_async16(dst + (uint32_t)(8 * i * kRowPitch), p, ok ? 16u : 0u);
+          const unsigned char* p = feat + (size_t)(ok ? src[i] : 0) * kRowBytes + src_byte;
+          cp_async16(dst_lane + st + (uint32_t)(i * 1024), p, ok ? 16u : 0u);
         }
-        cp_async_arrive_noinc(&sfull[s]);
-        if (gt == 0) {
-          smeta[s].last = (mask == 0);
-          smeta[s].end = 0;
-          mbar_arrive(&sfull[s]);  // release: publishes the meta write
-        }
+        cp_async_commit();
         q++;
+        if (q - q_arrived > (uint32_t)C::kInFlight) {
+          cp_async_wait<C::kInFlight>();  // the oldest pending group has landed
+          fence_proxy_async();            // generic-proxy writes -> visible to the tensor core's async proxy
+          mbar_arrive(&full[q_arrived % C::kStages]);
+          q_arrived++;
+        }
       }
     }
-    // two termination slots, one per converter group
-    for (int t = 0; t < kConvGroups; t++) {
-      const uint32_t s = q % C::kSStages;
-      mbar_wait(&sempty[s], ((q / C::kSStages) & 1u) ^ 1u);
-      cp_async_arrive_noinc(&sfull[s]);
+    cp_async_wait<0>();
+    fence_proxy_async();
+    while (q_arrived < q) {
+      mbar_arrive(&full[q_arrived % C::kStages]);
+      q_arrived++;
+    }
+    {  // termination slot
+      const uint32_t s = q % C::kStages;
+      mbar_wait(&empty[s], ((q / C::kStages) & 1u) ^ 1u);
       if (gt == 0) {
-        smeta[s].last = 1;
-        smeta[s].end = 1 + t;
-        mbar_arrive(&sfull[s]);
+        meta[s].last = 1;
+        meta[s].end = 1;
+        mbar_arrive(&full[s]);  // stands in for the expect_tx arrival of a real slot
       }
-      q++;
-    }
-  } else {
-    // =========================== converters ===========================
-    const int cw = warp - kWarpConv0;
-    const int grp = cw / kConvWarps;
-    const bool leader = (cw % kConvWarps) == 0 && lane == 0;
-    const int my_row = 32 * (warp & 3) + lane;  // TMEM lane == tile row; a warp may only touch its lane quarter
-    const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
-    for (uint32_t q = grp;; q += kConvGroups) {
-      const uint32_t s = q % C::kSStages, as = q % C::kAStages;
-      mbar_wait(&sfull[s], (q / C::kSStages) & 1u);
-      const int m_last = smeta[s].last, m_end = smeta[s].end;
-      if (m_end) {
-        if (m_end == 1) {  // this group owns the slot number the MMA warp will look at next
-          mbar_wait(&empty_a[as], ((q / C::kAStages) & 1u) ^ 1u);
-          if (leader) {
-            meta[as].last = 1;
-            meta[as].end = 1;
-          }
-          mbar_arrive(&full_a[as]);
-        }
-        break;
-      }
-      mbar_wait(&empty_a[as], ((q / C::kAStages) & 1u) ^ 1u);
-      tc_fence_after();
-      if (leader) {
-        meta[as].last = m_last;
-        meta[as].end = 0;
-      }
-      const float4* rowp = reinterpret_cast<const float4*>(sring + (size_t)s * kStageBytes + (size_t)my_row * kRowPitch);
-      const uint32_t a_hi = tmem_base + lane_base + (uint32_t)(C::kAccCols + as * C::kAStageCols);
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        float own[16];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const float4 x = rowp[4 * j + u];
-          own[4 * u + 0] = x.x;
-          own[4 * u + 1] = x.y;
-          own[4 * u + 2] = x.z;
-          own[4 * u + 3] = x.w;
-        }
-        uint32_t hi[16], lo[16];
-#pragma unroll
-        for (int e = 0; e < 16; e++) {
-          const uint32_t h = __float_as_uint(own[e]) & 0xFFFFE000u;
-          hi[e] = h;
-          lo[e] = __float_as_uint(own[e] - __uint_as_float(h));
-        }
-        tmem_st16(a_hi + 16u * j, hi);
-        tmem_st16(a_hi + 64u + 16u * j, lo);
-      }
-      mbar_arrive(&sempty[s]);  // the row has been consumed (the TMEM stores depend on every load)
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      tc_fence_before();
-      mbar_arrive(&full_a[as]);  // release also orders the leader's meta write
+      mbar_arrive(&full[s]);
     }
   }
 
@@ -544,35 +443,56 @@ sparse_conv_tc_kernel(const float* __restrict__ feat, const unsigned char* __res
 }
 
 // One-time weight preparation: (KV, Cin, Cout) fp32 -> per offset group the exact shared-memory image the
-// kernel consumes: chunks x ([hi rows | lo rows] x 128 B), K-major, 128B-swizzled, tf32-split.
+// kernel consumes: [G1 rows | G2 rows] x 128 B, K-major, 128B-swizzled, bf16 split.
 __global__ void prepare_weights_kernel(const float* __restrict__ w, int KV, int Cin, int Cout,
                                        unsigned char* __restrict__ img) {
-  const int gk = 64 / Cin;                      // offsets stacked along K per image
+  const int gk = 64 / Cin;  // offsets stacked along K per image
   const int n_groups = (KV + gk - 1) / gk;
-  const size_t chunk_bytes = (size_t)2 * Cout * 128, per_group = 2 * chunk_bytes;
+  const size_t per_group = (size_t)2 * Cout * 128;
   const int total = n_groups * Cout * 64;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-    const int kl = e % 64;                      // K index inside the group image
+    const int kl = e % 64;  // K index inside the group image
     int t = e / 64;
     const int n = t % Cout;
     const int g = t / Cout;
     const int kk = g * gk + kl / Cin, ci = kl % Cin;
     const float v = kk < KV ? w[((size_t)kk * Cin + ci) * Cout + n] : 0.f;
-    const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-    const float lo = v - hi;
-    const int ch = kl >> 5, kc = kl & 31;
-    // chunk-major; inside a chunk rows [0,Cout) = hi, rows [Cout, 2*Cout) = lo (Cout is a multiple of 8, so the
-    // lo rows start on an 8-row group boundary and keep the same (row & 7) swizzle phase)
-    const size_t off = (size_t)ch * chunk_bytes + (size_t)(n >> 3) * 1024 + (size_t)(n & 7) * 128 +
-                       (size_t)((((kc >> 2) ^ (n & 7)) << 4) + (kc & 3) * 4);
-    *reinterpret_cast<float*>(img + (size_t)g * per_group + off) = hi;
-    *reinterpret_cast<float*>(img + (size_t)g * per_group + (size_t)Cout * 128 + off) = lo;
+    const __nv_bfloat16 g1 = __float2bfloat16_rn(v);
+    const __nv_bfloat16 g2 = __float2bfloat16_rn(v - __bfloat162float(g1));
+    // rows [0,Cout) = g1, rows [Cout, 2*Cout) = g2 (Cout is a multiple of 8, so the g2 rows start on an 8-row
+    // group boundary and keep the same (row & 7) swizzle phase)
+    const size_t off = (size_t)(n >> 3) * 1024 + (size_t)(n & 7) * 128 + (size_t)((((kl >> 3) ^ (n & 7)) << 4) + (kl & 7) * 2);
+    *reinterpret_cast<__nv_bfloat16*>(img + (size_t)g * per_group + off) = g1;
+    *reinterpret_cast<__nv_bfloat16*>(img + (size_t)g * per_group + (size_t)Cout * 128 + off) = g2;
+  }
+}
+
+// fp32 feature rows -> packed rows [h1 | h2] (one thread per 8 channels)
+__global__ void feature_pack_kernel(const float* __restrict__ feat, const int* __restrict__ n_rows_ptr, int cap, int C,
+                                    unsigned char* __restrict__ packed) {
+  const int n_rows = min(*n_rows_ptr, cap);
+  const int upr = C / 8;
+  const long long total = (long long)n_rows * upr;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / upr;
+    const int u = (int)(e % upr);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(feat + r * C + u * 8));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(feat + r * C + u * 8 + 4));
+    uint32_t h1[4], h2[4];
+    split2(a.x, a.y, h1[0], h2[0]);
+    split2(a.z, a.w, h1[1], h2[1]);
+    split2(b.x, b.y, h1[2], h2[2]);
+    split2(b.z, b.w, h1[3], h2[3]);
+    unsigned char* prow = packed + r * (4 * C) + u * 16;
+    *reinterpret_cast<uint4*>(prow) = make_uint4(h1[0], h1[1], h1[2], h1[3]);
+    *reinterpret_cast<uint4*>(prow + 2 * C) = make_uint4(h2[0], h2[1], h2[2], h2[3]);
   }
 }
 
 template <int CIN, int COUT>
-int launch_tc(const float* feat, const unsigned char* wprep, const int* nbr, int nbr_stride, const int* n_out,
-              int out_cap, int KV, const float* scale, const float* shift, int relu, float* out, cudaStream_t st) {
+int launch_tc(const unsigned char* feat, const unsigned char* wprep, const int* nbr, int nbr_stride, const int* n_out,
+              int out_cap, int KV, const float* scale, const float* shift, int relu, float* out,
+              unsigned char* out_packed, cudaStream_t st) {
   using C = TcCfg<CIN, COUT>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -583,7 +503,7 @@ int launch_tc(const float* feat, const unsigned char* wprep, const int* nbr, int
   const int tiles_cap = ceil_div(out_cap, kTileM);
   const int grid = tiles_cap < kNumSMs ? (tiles_cap > 0 ? tiles_cap : 1) : kNumSMs;
   sparse_conv_tc_kernel<CIN, COUT><<<grid, kThreads, C::kSmemBytes, st>>>(feat, wprep, nbr, nbr_stride, n_out, out_cap,
-                                                                         KV, scale, shift, relu, out);
+                                                                         KV, scale, shift, relu, out, out_packed);
   return check_launch();
 }
 
@@ -599,7 +519,7 @@ using namespace v3d;
 extern "C" size_t v3d_sparse_conv_prepared_bytes(int kernel_volume, int Cin, int Cout) {
   if (!tc_supported(kernel_volume, Cin, Cout)) return 0;  // 0 = this shape runs on the exact-fp32 SIMT path
   const int gk = 64 / Cin;  // offsets per image (K = 64 per pipeline slot)
-  return (size_t)((kernel_volume + gk - 1) / gk) * 2 * (2 * Cout * 128);
+  return (size_t)((kernel_volume + gk - 1) / gk) * (2 * Cout * 128);
 }
 
 extern "C" int v3d_sparse_conv_prepare(const float* weight, int kernel_volume, int Cin, int Cout, void* prepared,
@@ -614,21 +534,37 @@ extern "C" int v3d_sparse_conv_prepare(const float* weight, int kernel_volume, i
   return check_launch();
 }
 
-extern "C" int v3d_sparse_conv_fwd_tc(const float* feat, const void* prepared, const int* nbr, int nbr_stride,
+extern "C" int v3d_feature_pack(const float* feat, const int* n_rows, int capacity, int C, void* packed,
+                                v3d_stream_t stream) {
+  if (!feat || !n_rows || !packed || capacity <= 0) return V3D_ERR_INVALID_ARGUMENT;
+  if (C != 16 && C != 32 && C != 64) return V3D_ERR_INVALID_ARGUMENT;
+  if ((reinterpret_cast<uintptr_t>(feat) & 15) || (reinterpret_cast<uintptr_t>(packed) & 15)) return V3D_ERR_INVALID_ARGUMENT;
+  const long long units = (long long)capacity * (C / 8);
+  const long long want = (units + 255) / 256, cap_blocks = (long long)kNumSMs * 8;
+  const int blocks = (int)(want < cap_blocks ? want : cap_blocks);
+  feature_pack_kernel<<<blocks, 256, 0, as_stream(stream)>>>(feat, n_rows, capacity, C, static_cast<unsigned char*>(packed));
+  return check_launch();
+}
+
+extern "C" int v3d_sparse_conv_fwd_tc(const void* feat_packed, const void* prepared, const int* nbr, int nbr_stride,
                                       const int* n_out, int out_capacity, int kernel_volume, int Cin, int Cout,
-                                      const float* scale, const float* shift, int relu, float* out,
+                                      const float* scale, const float* shift, int relu, float* out, void* out_packed,
                                       v3d_stream_t stream) {
-  if (!feat || !prepared || !nbr || !n_out || !out) return V3D_ERR_INVALID_ARGUMENT;
+  if (!feat_packed || !prepared || !nbr || !n_out || (!out && !out_packed)) return V3D_ERR_INVALID_ARGUMENT;
   if (out_capacity <= 0 || kernel_volume <= 0 || nbr_stride < out_capacity) return V3D_ERR_INVALID_ARGUMENT;
   if ((scale == nullptr) != (shift == nullptr)) return V3D_ERR_INVALID_ARGUMENT;
   if (!tc_supported(kernel_volume, Cin, Cout)) return V3D_ERR_INVALID_ARGUMENT;
-  if ((reinterpret_cast<uintptr_t>(prepared) & 15) || (reinterpret_cast<uintptr_t>(feat) & 15))
+  if ((reinterpret_cast<uintptr_t>(prepared) & 15) || (reinterpret_cast<uintptr_t>(feat_packed) & 15) ||
+      (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(out_packed) & 15))
     return V3D_ERR_INVALID_ARGUMENT;
+  const unsigned char* fp = static_cast<const unsigned char*>(feat_packed);
   const unsigned char* wp = static_cast<const unsigned char*>(prepared);
+  unsigned char* op = static_cast<unsigned char*>(out_packed);
   cudaStream_t st = as_stream(stream);
-#define V3D_TC_CASE(CI, CO)                                                                                       \
-  if (Cin == CI && Cout == CO)                                                                                    \
-    return launch_tc<CI, CO>(feat, wp, nbr, nbr_stride, n_out, out_capacity, kernel_volume, scale, shift, relu, out, st);
+#define V3D_TC_CASE(CI, CO)                                                                                      \
+  if (Cin == CI && Cout == CO)                                                                                   \
+    return launch_tc<CI, CO>(fp, wp, nbr, nbr_stride, n_out, out_capacity, kernel_volume, scale, shift, relu, out, op, \
+                             st);
   V3D_TC_CASE(16, 16)
   V3D_TC_CASE(16, 32)
   V3D_TC_CASE(16, 64)

@@ -262,7 +262,7 @@ def rulebook_conv(in_table, indices, n_rows, batch_size, shape, ksize, stride, p
 
 
 class PreparedWeights:
-    """Per-layer weight image for the tcgen05 path (hi/lo tf32 split, K-major, 128B-swizzled), built once.
+    """Per-layer weight image for the tcgen05 path (bf16 3-term split, K-major, 128B-swizzled), built once.
     `.buf` is None when the shape is only supported by the exact-fp32 SIMT path (e.g. Cin = 4)."""
 
     def __init__(self, weight):
@@ -280,22 +280,61 @@ class PreparedWeights:
                       "v3d_sparse_conv_prepare")
 
 
-def sparse_conv(feat, weight, nbr, n_out, out_capacity, scale=None, shift=None, relu=False, out=None):
+def _rows_of(feat, n_out, nbr):
+    """Device int32 row count to convert when packing on the fly: every row of `feat` (the input row count is
+    not an argument of the conv; rows past it are never gathered)."""
+    return torch.full((1,), feat.shape[0], dtype=torch.int32, device=feat.device)
+
+
+def pack_features(feat, n_rows, out=None):
+    """fp32 rows (cap, C) -> packed rows (cap, 2*C) bf16 = [h1 | h2] with h1 = bf16(x), h2 = bf16(x - h1):
+    the operand format of the tensor-core sparse conv (v3d_feature_pack)."""
+    cap, c = feat.shape
+    if out is None:
+        out = torch.empty((cap, 2 * c), dtype=torch.bfloat16, device=feat.device)
+    assert out.shape == (cap, 2 * c) and out.dtype == torch.bfloat16 and feat.dtype == _F32
+    with torch.cuda.device(feat.device):
+        check(_lib.load().v3d_feature_pack(feat.data_ptr(), n_rows.data_ptr(), int(cap), int(c), out.data_ptr(),
+                                           _stream()), "v3d_feature_pack")
+    return out
+
+
+def unpack_features(packed):
+    """packed rows (rows, 2*C) bf16 -> fp32 (rows, C) = h1 + h2 (tests / debugging)."""
+    c = packed.shape[1] // 2
+    return packed[:, :c].float() + packed[:, c:].float()
+
+
+def sparse_conv(feat, weight, nbr, n_out, out_capacity, scale=None, shift=None, relu=False, out=None,
+                out_packed=None, write_f32=True):
     """feat (rows, Cin); weight (KV, Cin, Cout) / spconv's (k0,k1,k2,Cin,Cout) -> exact-fp32 SIMT kernel,
-    or a PreparedWeights -> tcgen05 3xTF32 kernel when the shape supports it; nbr (KV, stride)."""
+    or a PreparedWeights -> tcgen05 bf16x3 kernel when the shape supports it; nbr (KV, stride).
+
+    Tensor-core path: `feat` may be fp32 (packed on the fly, one extra kernel) or an already packed bf16
+    (rows, 2*Cin) tensor; `out_packed` (out_capacity, 2*Cout) bf16 receives the packed result for the next
+    layer, `write_f32=False` skips the fp32 rows (then `out_packed` is returned)."""
     if isinstance(weight, PreparedWeights):
         pw = weight
-        if out is None:
-            out = torch.empty((out_capacity, pw.cout), dtype=_F32, device=feat.device)
         if pw.buf is not None:
+            if feat.dtype != torch.bfloat16:
+                feat = pack_features(feat, _rows_of(feat, n_out, nbr))
+            assert feat.shape[1] == 2 * pw.cin
+            if write_f32 and out is None:
+                out = torch.empty((out_capacity, pw.cout), dtype=_F32, device=feat.device)
+            if not write_f32:
+                out = None
+                assert out_packed is not None
             with torch.cuda.device(feat.device):
                 check(_lib.load().v3d_sparse_conv_fwd_tc(
                     feat.data_ptr(), pw.buf.data_ptr(), nbr.data_ptr(), nbr.shape[1], n_out.data_ptr(),
                     int(out_capacity), pw.kv, pw.cin, pw.cout, scale.data_ptr() if scale is not None else None,
-                    shift.data_ptr() if shift is not None else None, int(bool(relu)), out.data_ptr(), _stream()),
+                    shift.data_ptr() if shift is not None else None, int(bool(relu)),
+                    out.data_ptr() if out is not None else None,
+                    out_packed.data_ptr() if out_packed is not None else None, _stream()),
                     "v3d_sparse_conv_fwd_tc")
-            return out
+            return out if out is not None else out_packed
         weight = pw.weight
+        assert feat.dtype == _F32, "the exact-fp32 path takes fp32 rows"
     cin, cout = weight.shape[-2], weight.shape[-1]
     kv = weight.numel() // (cin * cout)
     if out is None:

@@ -358,6 +358,9 @@ class SecondEngine:
         cmax = [16, 32, 64, 64, 64]
         self.feat = [[torch.empty((self.caps[lv], cmax[lv]), dtype=torch.float32, device=dev) for _ in range(2)]
                      for lv in range(5)]
+        # packed (bf16 h1|h2) twins for the tensor-core layers: two ping-pong buffers + one for packing fp32 input
+        self.featp = [[torch.empty((self.caps[lv], 2 * cmax[lv]), dtype=torch.bfloat16, device=dev)
+                       for _ in range(3 if lv == 0 else 2)] for lv in range(5)] if tensor_cores else None
         self.dense_out = torch.empty((B, 64, *shapes[4]), dtype=torch.float32, device=dev)
         self.dense_ws = torch.empty(ops._lib.load().v3d_sparse_to_dense_workspace_bytes(B, ops.i3(shapes[4])),
                                     dtype=torch.uint8, device=dev)
@@ -438,24 +441,44 @@ class SecondEngine:
             # entered the level); SubM layers ping-pong between the level's two buffers
             cur = 0 if lv == 0 else 1
             k = 0
+
+            def conv_op(name, d, x, nbr, n_rows_out, cap_out, lv_out, buf, last, lv=lv):
+                """One fused conv layer. Tensor-core layers consume and produce PACKED rows (the packed twin
+                of the fp32 buffer, same bytes); fp32 rows are only written where something reads them: the
+                exact-fp32 first layer and the last layer (-> dense BEV)."""
+                out32 = self.feat[lv_out][buf]
+                assert out32.shape[1] == d["cout"]
+                tc = isinstance(d["w"], ops.PreparedWeights) and d["w"].buf is not None
+                if not tc:
+                    assert x.dtype == torch.float32 and out32.data_ptr() != x.data_ptr()
+                    plan.append((name, 1, (lambda: ops.sparse_conv(x, d["w"], nbr, n_rows_out, cap_out, d["scale"],
+                                                                    d["shift"], True, out=out32))))
+                    return out32
+                if x.dtype != torch.bfloat16:  # fp32 rows from the SIMT layer -> packed operand format
+                    xp = self.featp[lv][2]
+                    plan.append(("pack_L%d" % lv, 1, (lambda x=x, xp=xp, lv=lv: ops.pack_features(
+                        x, self.n_rows[lv], out=xp))))
+                    x = xp
+                outp = self.featp[lv_out][buf]
+                assert outp.data_ptr() != x.data_ptr()
+                plan.append((name, 1, (lambda x=x: ops.sparse_conv(
+                    x, d["w"], nbr, n_rows_out, cap_out, d["scale"], d["shift"], True,
+                    out=out32 if last else None, out_packed=None if last else outp, write_f32=last))))
+                return out32 if last else outp
+
             while self.layers[li]["kind"] == "subm":
-                d, out = self.layers[li], self.feat[lv][cur]
-                assert out.shape[1] == d["cout"] and out.data_ptr() != x.data_ptr()
-                plan.append(("subm_L%d_%d_%dx%d" % (lv, k, d["cin"], d["cout"]), 1,
-                             (lambda x=x, d=d, out=out, lv=lv: ops.sparse_conv(
-                                 x, d["w"], self.nbr_subm[lv], self.n_rows[lv], self.caps[lv], d["scale"],
-                                 d["shift"], True, out=out))))
-                x, cur, li, k = out, cur ^ 1, li + 1, k + 1
-            d, out = self.layers[li], self.feat[lv + 1][0]
+                d = self.layers[li]
+                x = conv_op("subm_L%d_%d_%dx%d" % (lv, k, d["cin"], d["cout"]), d, x, self.nbr_subm[lv],
+                            self.n_rows[lv], self.caps[lv], lv, cur, False)
+                cur, li, k = cur ^ 1, li + 1, k + 1
+            d = self.layers[li]
             plan.append(("rulebook_conv_L%d" % lv, 5, (lambda d=d, lv=lv, index=index: ops.rulebook_conv(
                 index, self.indices[lv], self.n_rows[lv], B, self.shapes[lv], d["ks"], d["stride"],
                 d["pad"], d["dil"], self.caps[lv + 1], self.indices[lv + 1], self.n_rows[lv + 1],
                 self.nbr_conv[lv], self.conv_ws[lv]))))
-            plan.append(("sconv_L%d_%dx%d" % (lv, d["cin"], d["cout"]), 1,
-                         (lambda x=x, d=d, out=out, lv=lv: ops.sparse_conv(
-                             x, d["w"], self.nbr_conv[lv], self.n_rows[lv + 1], self.caps[lv + 1], d["scale"],
-                             d["shift"], True, out=out))))
-            x, li = out, li + 1
+            x = conv_op("sconv_L%d_%dx%d" % (lv, d["cin"], d["cout"]), d, x, self.nbr_conv[lv], self.n_rows[lv + 1],
+                        self.caps[lv + 1], lv + 1, 0, li == len(self.layers) - 1)
+            li += 1
         if self.rpn_mode == "fused_nhwc":
             # BEV map written directly in channels_last memory (what cuDNN's sm_100 kernels consume)
             sh = self.shapes[4]
