@@ -13,20 +13,20 @@
 // 16-byte cp.async straight into the 128B-swizzled K-major A tiles the MMAs read from shared memory.
 // No conversion pass, no register staging, no TMEM operand.
 //
-// One persistent CTA per SM, warp specialised (288 threads):
+// One persistent CTA per SM, warp specialised (672 threads):
 //   warps 0-3  epilogue   : tcgen05.ld the 128 x COUT fp32 accumulator halves (lane = output row), add
 //                           them, apply scale/shift/ReLU, store the row as fp32 and/or packed bf16x2
 //   warp  4    MMA issuer : warp-uniform loop, one elected lane issues per pipeline slot (K = 64) 2*4
 //                           tcgen05.mma, M=128, K=16, both operands from shared memory:
 //                           A_h1 * [G1 | G2] (N = 2*COUT) and A_h2 * G1 (N = COUT); tcgen05.commit frees
 //                           the stage and publishes the accumulator through mbarriers
-//   warps 5-8  fetchers   : stage the tile's rule rows in shared memory (the next tile's are prefetched
+//   warps 5-20 fetchers   : stage the tile's rule rows in shared memory (the next tile's are prefetched
 //                           into registers), find the kernel offsets the tile uses, and for every slot
 //                           gather the neighbour rows (zero-fill for missing neighbours) with cp.async into
 //                           the stage's A tiles while one thread streams the slot's weight image with a
-//                           1-D TMA bulk copy. cp.async groups complete kStages-1 slots later
-//                           (wait_group + fence.proxy.async + mbarrier arrive), so that many slots of
-//                           global-load latency are in flight.
+//                           1-D TMA bulk copy. Completion is asynchronous (cp.async.mbarrier.arrive on the
+//                           stage's full barrier), so up to kStages slots of global-load latency are in
+//                           flight and the fetchers never wait for their own loads.
 // Measured instruction costs on B200 (scripts/mma_probe.cu): one M=128 MMA costs max(47, N/2) clk for
 // every operand kind/source, so a slot is 4*(64+47) = 444 clk for COUT = 64 (3xTF32 needed 888).
 // Output rows are written exactly once (no atomics, deterministic).
@@ -37,15 +37,16 @@
 // TMEM columns: two accumulator buffers of 2*COUT columns: [h1*g1 + h2*g1 | h1*g2].
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace v3d {
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kEpiWarps = 4, kFetchWarps = 4;
+constexpr int kEpiWarps = 4;
 constexpr int kWarpMma = kEpiWarps, kWarpFetch0 = kEpiWarps + 1;
-constexpr int kThreads = 32 * (kWarpFetch0 + kFetchWarps);  // 288
 constexpr int kMaxKV = 27;
 constexpr int kATileBytes = kTileM * 128;  // 128 rows x 64 bf16
 constexpr int kABytes = 2 * kATileBytes;   // h1 tile | h2 tile
@@ -88,10 +89,12 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+__device__ __forceinline__ void cp_async16_cg(uint32_t dst, const void* src, uint32_t src_bytes) {  // L1 bypass
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// the mbarrier receives one arrival once all cp.async issued so far by this thread have landed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -177,7 +180,6 @@ struct TcCfg {
   static constexpr int kBBytes = 2 * COUT * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;   // multiple of 1024
   static constexpr int kStages = COUT == 64 ? 4 : 5;
-  static constexpr int kInFlight = kStages - 1;           // cp.async groups pending per fetch thread
   static constexpr int kAccBufCols = 2 * COUT;            // [h1*g1 + h2*g1 | h1*g2]
   static constexpr int kTmemCols = pow2_cols(2 * kAccBufCols);
   static constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * kStageBytes +
@@ -192,12 +194,12 @@ struct SlotMeta {
   int end;   // 1 = all tiles done
 };
 
-template <int CIN, int COUT>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int CIN, int COUT, int kFetchWarps>
+__global__ void __launch_bounds__(32 * (kWarpFetch0 + kFetchWarps), 1)
 sparse_conv_tc_kernel(const unsigned char* __restrict__ feat, const unsigned char* __restrict__ wprep,
                       const int* __restrict__ nbr, int nbr_stride, const int* __restrict__ n_out_ptr, int out_cap,
                       int KV, const float* __restrict__ scale, const float* __restrict__ shift, int relu,
-                      float* __restrict__ out, unsigned char* __restrict__ out_packed) {
+                      float* __restrict__ out, unsigned char* __restrict__ out_packed, int bypass_l1) {
   using C = TcCfg<CIN, COUT>;
   extern __shared__ unsigned char smem_raw[];
   // round up to 1024 B (SWIZZLE_128B atoms) by OFFSETTING the __shared__ array: casting through an integer
@@ -222,7 +224,7 @@ sparse_conv_tc_kernel(const unsigned char* __restrict__ feat, const unsigned cha
 
   if (tid == 0) {
     for (int s = 0; s < C::kStages; s++) {
-      mbar_init(&full[s], kFetchWarps * 32 + 1);  // every fetch thread + the expect_tx arrival of the B copy
+      mbar_init(&full[s], kFetchWarps * 32 + 1);  // every fetch thread's copies + the expect_tx arrival (B image)
       mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; a++) {
@@ -232,7 +234,7 @@ sparse_conv_tc_kernel(const unsigned char* __restrict__ feat, const unsigned cha
     fmask[0] = fmask[1] = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int c = tid; c < COUT; c += kThreads) {
+  for (int c = tid; c < COUT; c += (int)blockDim.x) {
     s_scale[c] = scale ? __ldg(&scale[c]) : 1.0f;
     s_shift[c] = shift ? __ldg(&shift[c]) : 0.0f;
   }
@@ -321,7 +323,8 @@ sparse_conv_tc_kernel(const unsigned char* __restrict__ feat, const unsigned cha
           mbar_wait(&acc_empty[a], ((it >> 1) & 1) ^ 1);
           tile_open = true;
         }
-        tc_fence_after();
+        fence_proxy_async();  // the A tiles were written by cp.async (generic proxy), the MMAs read them through
+        tc_fence_after();     // the async proxy
         const uint32_t st = ring_u32 + s * (uint32_t)C::kStageBytes;
         const uint64_t da1 = make_desc(st), da2 = make_desc(st + kATileBytes), db0 = make_desc(st + kABytes);
         const uint32_t d = tmem_base + (uint32_t)(a * C::kAccBufCols);
@@ -353,27 +356,37 @@ sparse_conv_tc_kernel(const unsigned char* __restrict__ feat, const unsigned cha
     const int rsub = lane >> 4, part = (lane >> 3) & 1, unit = lane & 7;
     const int off = (unit * 8) / CIN;
     const int src_byte = part * (2 * CIN) + ((unit * 8) % CIN) * 2;
-    const int row0 = fw * 2 + rsub;  // this lane copies rows row0 + 8 i; (row & 7) == row0
-    const uint32_t dst_lane = smem_u32(ring) + (uint32_t)(part * kATileBytes + row0 * 128 + ((unit ^ row0) << 4));
+    constexpr int kRowStep = 2 * kFetchWarps, kRowsPerLane = kTileM / kRowStep;
+    const int row0 = fw * 2 + rsub;  // this lane copies rows row0 + kRowStep i; (row & 7) == (row0 & 7)
+    const uint32_t dst_lane =
+        smem_u32(ring) + (uint32_t)(part * kATileBytes + row0 * 128 + ((unit ^ (row0 & 7)) << 4));
 
-    int pre[kMaxKV];  // rule rows of the NEXT tile (row = gt), in flight while the current tile is fetched
+    // rule rows of the NEXT tile, in flight while the current tile is fetched: thread -> row gt % 128, offsets
+    // kpart + kParts j (kpart = gt / 128 is warp-uniform)
+    constexpr int kParts = NF / kTileM, kPre = (kMaxKV + kParts - 1) / kParts;
+    const int srow = gt & (kTileM - 1), kpart = gt >> 7;
+    int pre[kPre];
     auto prefetch = [&](int tile) {
-      const int o = tile * kTileM + gt;
+      const int o = tile * kTileM + srow;
       const bool ok = tile < n_tiles && o < n_out;
 #pragma unroll
-      for (int k = 0; k < kMaxKV; k++) pre[k] = (ok && k < KV) ? __ldg(nbr + (size_t)k * nbr_stride + o) : -1;
+      for (int j = 0; j < kPre; j++) {
+        const int k = kpart + kParts * j;
+        pre[j] = (ok && k < KV) ? __ldg(nbr + (size_t)k * nbr_stride + o) : -1;
+      }
     };
     prefetch(blockIdx.x);
-    uint32_t q = 0, q_arrived = 0;  // slots issued / slots whose copies were published to the MMA warp
+    uint32_t q = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
       asm volatile("bar.sync 1, %0;" ::"n"(NF) : "memory");  // all copies that read idx_tile are issued
       if (gt == 0) fmask[(it + 1) & 1] = 0u;
       uint32_t mine = 0;
 #pragma unroll
-      for (int k = 0; k < kMaxKV; k++) {
-        if (k < KV) idx_tile[k * kTileM + gt] = pre[k];
-        if (__any_sync(0xffffffffu, pre[k] >= 0)) mine |= 1u << k;
+      for (int j = 0; j < kPre; j++) {
+        const int k = kpart + kParts * j;
+        if (k < KV) idx_tile[k * kTileM + srow] = pre[j];
+        if (__any_sync(0xffffffffu, pre[j] >= 0)) mine |= 1u << k;
       }
       if (lane == 0 && mine) atomicOr(&fmask[it & 1], mine);
       asm volatile("bar.sync 1, %0;" ::"n"(NF) : "memory");
@@ -396,30 +409,21 @@ sparse_conv_tc_kernel(const unsigned char* __restrict__ feat, const unsigned cha
         const int kk = g * C::kGK + off;
         const bool kv_ok = kk < KV;  // the last group of a layer may be padded with non-existent offsets
         const int* idx_row = idx_tile + (kv_ok ? kk : 0) * kTileM + row0;
-        int src[16];
+        int src[kRowsPerLane];
 #pragma unroll
-        for (int i = 0; i < 16; i++) src[i] = idx_row[8 * i];
+        for (int i = 0; i < kRowsPerLane; i++) src[i] = idx_row[kRowStep * i];
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
+        for (int i = 0; i < kRowsPerLane; i++) {
           const bool ok = kv_ok && src[i] >= 0;
           const unsigned char* p = feat + (size_t)(ok ? src[i] : 0) * kRowBytes + src_byte;
-          cp_async16(dst_lane + st + (uint32_t)(i * 1024), p, ok ? 16u : 0u);
+          if (bypass_l1)
+            cp_async16_cg(dst_lane + st + (uint32_t)(i * kRowStep * 128), p, ok ? 16u : 0u);
+          else
+            cp_async16(dst_lane + st + (uint32_t)(i * kRowStep * 128), p, ok ? 16u : 0u);
         }
-        cp_async_commit();
+        cp_async_arrive_noinc(&full[s]);  // arrives when this thread's copies have landed
         q++;
-        if (q - q_arrived > (uint32_t)C::kInFlight) {
-          cp_async_wait<C::kInFlight>();  // the oldest pending group has landed
-          fence_proxy_async();            // generic-proxy writes -> visible to the tensor core's async proxy
-          mbar_arrive(&full[q_arrived % C::kStages]);
-          q_arrived++;
-        }
       }
-    }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    while (q_arrived < q) {
-      mbar_arrive(&full[q_arrived % C::kStages]);
-      q_arrived++;
     }
     {  // termination slot
       const uint32_t s = q % C::kStages;
@@ -495,15 +499,27 @@ int launch_tc(const unsigned char* feat, const unsigned char* wprep, const int* 
               unsigned char* out_packed, cudaStream_t st) {
   using C = TcCfg<CIN, COUT>;
   static bool attr_set = false;
+  static int fetch_warps = 8, bypass_l1 = 0;
   if (!attr_set) {
-    V3D_CUDA_TRY(cudaFuncSetAttribute(sparse_conv_tc_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    V3D_CUDA_TRY(cudaFuncSetAttribute(sparse_conv_tc_kernel<CIN, COUT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)C::kSmemBytes));
+    V3D_CUDA_TRY(cudaFuncSetAttribute(sparse_conv_tc_kernel<CIN, COUT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)C::kSmemBytes));
+    V3D_CUDA_TRY(cudaFuncSetAttribute(sparse_conv_tc_kernel<CIN, COUT, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)C::kSmemBytes));
+    if (const char* e = getenv("V3D_TC_FETCH_WARPS")) fetch_warps = atoi(e);  // tuning knobs: 4, 8 or 16
+    if (const char* e = getenv("V3D_TC_BYPASS_L1")) bypass_l1 = atoi(e);
     attr_set = true;
   }
   const int tiles_cap = ceil_div(out_cap, kTileM);
   const int grid = tiles_cap < kNumSMs ? (tiles_cap > 0 ? tiles_cap : 1) : kNumSMs;
-  sparse_conv_tc_kernel<CIN, COUT><<<grid, kThreads, C::kSmemBytes, st>>>(feat, wprep, nbr, nbr_stride, n_out, out_cap,
-                                                                         KV, scale, shift, relu, out, out_packed);
+#define V3D_TC_LAUNCH(FW)                                                                                          \
+  sparse_conv_tc_kernel<CIN, COUT, FW><<<grid, 32 * (kWarpFetch0 + FW), C::kSmemBytes, st>>>(                      \
+      feat, wprep, nbr, nbr_stride, n_out, out_cap, KV, scale, shift, relu, out, out_packed, bypass_l1)
+  if (fetch_warps == 4) V3D_TC_LAUNCH(4);
+  else if (fetch_warps == 16) V3D_TC_LAUNCH(16);
+  else V3D_TC_LAUNCH(8);
+#undef V3D_TC_LAUNCH
   return check_launch();
 }
 
