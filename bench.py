@@ -325,6 +325,14 @@ def run_b200(args):
                     "launches": g["n"], "avg_us_per_launch": round(g["us"] / g["n"], 2),
                     "alg_bytes_per_launch": int(g["bytes"] / g["n"]),
                     "share_of_step": round(g["us"] / step_us, 4)}
+        # measured DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) comes from the committed
+        # `ncu --set full` capture of the same workload (scripts/summarize_ncu.py -> profiles/traffic.json)
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            t = json.load(open(tpath)).get(fam)
+            if t:
+                roofline["traffic"] = int(t["dram_bytes_per_launch"])
+                roofline["traffic_source"] = t.get("source")
         vox = [r for r in table if r["op"].startswith("voxelize")][0]
         dn = [r for r in table if r["op"].startswith("dense")][0]
         extra_roof = {"voxelize+scatter": {"gbs": vox["gbs"], "frac": round(vox["gbs"] / hbm_peak, 4)},

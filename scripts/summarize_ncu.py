@@ -93,5 +93,33 @@ def full(path):
             print("| %s | parse error %s |" % (r.get("Kernel Name", "?")[:40], e))
 
 
+FAMILIES = [("sparse_conv_fwd", ("sparse_conv_tc_kernel", "sparse_conv_kernel")), ("voxelize+vfe", ("vox_",)),
+            ("dense", ("dense_",)), ("nms_rotated", ("nms_",)), ("rulebook", ("rule_", "conv_mark", "conv_scan", "conv_rank"))]
+
+
+def traffic(path, tag=None):
+    """profiles/traffic.json: measured DRAM bytes (read + write) per launch for each kernel family, averaged over
+    the launches of the capture -- bench.py copies the dominant family's figure into roofline.traffic."""
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.DictReader(io.StringIO(out[out.index('"ID"'):])))
+    units, rows = rows[0], rows[1:]
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    res = {}
+    for fam, keys in FAMILIES:
+        tot, n, us = 0.0, 0, 0.0
+        for r in rows:
+            if any(k in r["Kernel Name"] for k in keys):
+                for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    tot += float(r[m].replace(",", "")) * scale.get(units[m], 1.0)
+                t = float(r["gpu__time_duration.sum"].replace(",", ""))
+                us += t / 1e3 if units["gpu__time_duration.sum"] in ("ns", "nsecond") else t
+                n += 1
+        if n:
+            res[fam] = {"dram_bytes_per_launch": int(tot / n), "launches": n, "avg_us_under_ncu": round(us / n, 1),
+                        "source": tag or path}
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])
