@@ -93,7 +93,7 @@ def full(path):
             print("| %s | parse error %s |" % (r.get("Kernel Name", "?")[:40], e))
 
 
-FAMILIES = [("sparse_conv_fwd", ("sparse_conv_tc_kernel", "sparse_conv_kernel")), ("voxelize+vfe", ("vox_",)),
+FAMILIES = [("sparse_conv_fwd", ("sparse_conv_",)), ("voxelize+vfe", ("vox_",)),
             ("dense", ("dense_",)), ("nms_rotated", ("nms_",)), ("rulebook", ("rule_", "conv_mark", "conv_scan", "conv_rank"))]
 
 

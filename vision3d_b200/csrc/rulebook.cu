@@ -124,8 +124,8 @@ struct ConvWs {
   unsigned int* bitmap;  // cells/32 words
   int* l1;               // per 1024 cells: count, then exclusive prefix inside its level-2 group
   int* l2;               // per 1024 l1 entries: count, then exclusive prefix
-  unsigned int* uniq;    // unique marked cells, arbitrary order
-  int* n_uniq;
+  unsigned int* uniq;    // reserved (was: append list of marked cells; the bitmap is enumerated instead)
+  int* n_uniq;           // reserved
   size_t n_words, n_l1, n_l2;
   size_t zero_bytes;  // prefix of the workspace that must be zeroed per call
   size_t total;
@@ -153,61 +153,48 @@ inline ConvWs conv_layout(void* base, unsigned long long cells, int out_capacity
   return w;
 }
 
+// Marks every output cell some input row reaches. Fire-and-forget RED.OR only: no returned value, no global
+// append list, no per-group counter (an earlier version appended "fresh" cells to a list through ONE global
+// counter -- tens of thousands of same-address atomics, 80-130 us per level; the counts and the cell
+// enumeration now come from the bitmap itself).
 __global__ void __launch_bounds__(256) conv_mark_kernel(const int4* __restrict__ idx,
                                                         const int* __restrict__ n_rows, int cap_rows,
-                                                        ConvGeom G, ConvWs W, int out_capacity) {
+                                                        ConvGeom G, ConvWs W) {
   const int n = min(*n_rows, cap_rows);
-  const int lane = threadIdx.x & 31;
-  // one thread per input row walks the kernel offsets (only ~1/stride^3 of them reach an output cell);
-  // warp-uniform trip counts so that the append can be aggregated with one atomic per warp and offset
-  for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += gridDim.x * blockDim.x) {
-    const int i = i0 + lane;
-    const int4 c = i < n ? idx[i] : make_int4(0, 0, 0, 0);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int4 c = idx[i];
     for (int kz = 0; kz < G.ks[0]; kz++) {
       const int nz = c.y + G.pad[0] - kz * G.dil[0];
       const int oz = nz / G.stride[0];
-      const bool z_ok = nz >= 0 && (nz - oz * G.stride[0]) == 0 && oz < G.out_shape[0];
+      if (nz < 0 || (nz - oz * G.stride[0]) != 0 || oz >= G.out_shape[0]) continue;
       for (int ky = 0; ky < G.ks[1]; ky++) {
         const int ny = c.z + G.pad[1] - ky * G.dil[1];
         const int oy = ny / G.stride[1];
-        const bool zy_ok = z_ok && ny >= 0 && (ny - oy * G.stride[1]) == 0 && oy < G.out_shape[1];
-        if (!__any_sync(0xffffffffu, zy_ok && i < n)) continue;  // warp-uniform skip
+        if (ny < 0 || (ny - oy * G.stride[1]) != 0 || oy >= G.out_shape[1]) continue;
+        const size_t row_base = (((size_t)c.x * G.out_shape[0] + oz) * G.out_shape[1] + oy) * G.out_shape[2];
         for (int kx = 0; kx < G.ks[2]; kx++) {
           const int nx = c.w + G.pad[2] - kx * G.dil[2];
           const int ox = nx / G.stride[2];
-          const bool ok = i < n && zy_ok && nx >= 0 && (nx - ox * G.stride[2]) == 0 && ox < G.out_shape[2];
-          bool fresh = false;
-          unsigned int cell = 0;
-          if (ok) {
-            cell = (unsigned int)((((size_t)c.x * G.out_shape[0] + oz) * G.out_shape[1] + oy) * G.out_shape[2] + ox);
-            const unsigned int bit = 1u << (cell & 31);
-            const unsigned int old = atomicOr(&W.bitmap[cell >> 5], bit);
-            if (!(old & bit)) {
-              fresh = true;
-              atomicAdd(&W.l1[cell / kCoarse], 1);
-            }
-          }
-          const unsigned int m = __ballot_sync(0xffffffffu, fresh);
-          if (m) {
-            int base = 0;
-            if (lane == (__ffs(m) - 1)) base = atomicAdd(W.n_uniq, __popc(m));
-            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-            if (fresh) {
-              const int u = base + __popc(m & ((1u << lane) - 1u));
-              if (u < out_capacity) W.uniq[u] = cell;
-            }
-          }
+          if (nx < 0 || (nx - ox * G.stride[2]) != 0 || ox >= G.out_shape[2]) continue;
+          const unsigned int cell = (unsigned int)(row_base + ox);
+          atomicOr(&W.bitmap[cell >> 5], 1u << (cell & 31));
         }
       }
     }
   }
 }
 
-// in-place: l1[g*1024 .. +1024) -> exclusive prefix inside group g; l2[g] = group total
+// l1[i] = popcount of coarse group i (one 32-byte bitmap sector), then in place -> exclusive prefix inside the
+// 1024-group block g; l2[g] = block total
 __global__ void __launch_bounds__(1024) conv_scan_l1_kernel(ConvWs W) {
   __shared__ int sm[33];
   const size_t i = (size_t)blockIdx.x * 1024 + threadIdx.x;
-  int v = i < W.n_l1 ? W.l1[i] : 0;
+  int v = 0;
+  if (i < W.n_l1) {
+    const uint4* p = reinterpret_cast<const uint4*>(W.bitmap) + 2 * i;
+    const uint4 a = p[0], b = p[1];
+    v = __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w);
+  }
   int total;
   int ex = block_exclusive_scan(v, sm, total);
   if (i < W.n_l1) W.l1[i] = ex;
@@ -242,21 +229,43 @@ __device__ __forceinline__ int rank_of_cell(const ConvWs& W, unsigned int cell) 
   return rank;
 }
 
+// Output rows in ascending flat order: one thread per bitmap word walks its set bits; the row number of the
+// word's first active cell is the two-level prefix plus the popcounts of the earlier words of its sector.
 __global__ void __launch_bounds__(256) conv_rank_kernel(ConvWs W, ConvGeom G, int out_capacity,
                                                         int4* __restrict__ out_idx) {
-  const int n = min(*W.n_uniq, out_capacity);
-  for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
-    const unsigned int cell = W.uniq[u];
-    const int rank = rank_of_cell(W, cell);
-    if (rank >= 0 && rank < out_capacity) {
-      unsigned int r = cell;
-      int x = r % G.out_shape[2];
-      r /= G.out_shape[2];
-      int y = r % G.out_shape[1];
-      r /= G.out_shape[1];
-      int z = r % G.out_shape[0];
-      r /= G.out_shape[0];
-      out_idx[rank] = make_int4((int)r, z, y, x);
+  const size_t n_words = W.n_l1 * kWordsPerCoarse;
+  for (size_t wq = (size_t)blockIdx.x * blockDim.x + threadIdx.x; wq < n_words; wq += (size_t)gridDim.x * blockDim.x) {
+    unsigned int word = W.bitmap[wq];
+    if (word == 0u) continue;
+    const size_t g = wq / kWordsPerCoarse;
+    int rank = W.l2[g >> 10] + W.l1[g];
+    for (size_t w = g * kWordsPerCoarse; w < wq; w++) rank += __popc(W.bitmap[w]);
+    // decode the first cell once, then step along x (cells of one word are consecutive)
+    unsigned int r = (unsigned int)(wq * 32);
+    int x = r % G.out_shape[2];
+    r /= G.out_shape[2];
+    int y = r % G.out_shape[1];
+    r /= G.out_shape[1];
+    int z = r % G.out_shape[0];
+    int bidx = (int)(r / G.out_shape[0]);
+    int prev = 0;
+    while (word) {
+      const int bit = __ffs(word) - 1;
+      word &= word - 1;
+      x += bit - prev;
+      prev = bit;
+      while (x >= G.out_shape[2]) {  // carry into y / z / batch (at most a few times per word)
+        x -= G.out_shape[2];
+        if (++y == G.out_shape[1]) {
+          y = 0;
+          if (++z == G.out_shape[0]) {
+            z = 0;
+            bidx++;
+          }
+        }
+      }
+      if (rank < out_capacity) out_idx[rank] = make_int4(bidx, z, y, x);
+      rank++;
     }
   }
 }
@@ -428,10 +437,10 @@ static int rulebook_conv_impl(const void* in_table, const void* in_level_index, 
   cudaStream_t st = as_stream(stream);
   V3D_CUDA_TRY(cudaMemsetAsync(workspace, 0, W.zero_bytes, st));
   conv_mark_kernel<<<dim3(row_grid(capacity_rows)), 256, 0, st>>>(
-      reinterpret_cast<const int4*>(indices), n_rows, capacity_rows, G, W, out_capacity);
+      reinterpret_cast<const int4*>(indices), n_rows, capacity_rows, G, W);
   conv_scan_l1_kernel<<<(unsigned int)W.n_l2, 1024, 0, st>>>(W);
   conv_scan_l2_kernel<<<1, 1024, 0, st>>>(W, n_out);
-  conv_rank_kernel<<<row_grid(out_capacity), 256, 0, st>>>(W, G, out_capacity,
+  conv_rank_kernel<<<row_grid((int)(W.n_words < (1u << 30) ? W.n_words : (1u << 30))), 256, 0, st>>>(W, G, out_capacity,
                                                           reinterpret_cast<int4*>(out_indices));
   if (in_level_index) {
     const unsigned long long in_cells = (unsigned long long)B * shape_host[0] * shape_host[1] * shape_host[2];
