@@ -247,6 +247,24 @@ V3D_API int v3d_query_and_group(const float* xyz, const float* new_xyz, const fl
 V3D_API int v3d_second_head_decode(const float* reg_map, const long long* reg_strides_host, const float* anchors,
                                    const int64_t* anchor_idx, int B, int n_cls, int n_yaw, int ny, int nx,
                                    int topk, float* boxes, float* nms_in, v3d_stream_t stream);
+/* The same stage without materialising the head maps (detector/proposal.py:61-78 computes conv_cls and conv_reg
+ * over all ny*nx*n_yaw anchors and then keeps topk of them):
+ *   v3d_head_cls_logits  : 1x1 classification conv on the channels_last (B, ny, nx, 128) RPN map ->
+ *                          logits (B, n_out, ny*nx) [= conv_cls output, NCHW], n_out <= 8, weight (n_out,128)
+ *   v3d_topk_rows        : row-wise top-k, values descending, ties -> lower index (torch.topk semantics up to
+ *                          the order of equal values), k <= 256; sigmoid is monotonic, so it runs on logits
+ *   v3d_head_reg_gather  : conv_reg evaluated only at the topk anchors -> deltas (N,7); scores = sigmoid(logit)
+ *   v3d_second_head_decode_compact : decode + BEV + NMS group offsets from the compact deltas */
+V3D_API int v3d_head_cls_logits(const float* fmap_nhwc, int B, int hw, int C, const float* weight,
+                                const float* bias, int n_out, float* logits, v3d_stream_t stream);
+V3D_API int v3d_topk_rows(const float* values, int rows, int row_len, int k, float* out_values,
+                          int64_t* out_index, v3d_stream_t stream);
+V3D_API int v3d_head_reg_gather(const float* fmap_nhwc, int C, const float* w_reg, const float* b_reg,
+                                const float* top_logits, const int64_t* anchor_idx, int B, int n_cls, int n_yaw,
+                                int ny, int nx, int topk, float* deltas, float* scores, v3d_stream_t stream);
+V3D_API int v3d_second_head_decode_compact(const float* deltas, const float* anchors, const int64_t* anchor_idx,
+                                           int B, int n_cls, int n_yaw, int ny, int nx, int topk, float* boxes,
+                                           float* nms_in, v3d_stream_t stream);
 V3D_API int v3d_pack_detections(const float* boxes, const float* scores, const int64_t* keep, const int* count,
                                 const float* score_thresh, int N, int n_cls, int topk,
                                 const int* const* counters_dev, int n_counters, float* result,

@@ -228,3 +228,80 @@ def test_fused_head_kernels_match_torch_expressions(cuda, no_tf32):
     np.testing.assert_allclose(r0[:n_kept].numpy(), r1[:n_kept].numpy(), rtol=1e-5, atol=1e-4)
     np.testing.assert_array_equal(r0[:N, 10].numpy(), r1[:N, 10].numpy())   # valid flags
     np.testing.assert_array_equal(r0[N, :6].numpy(), r1[N, :6].numpy())     # counters row
+
+
+def test_topk_rows_matches_torch_topk(cuda):
+    from vision3d_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(3)
+    vals = torch.randn((6, 70400), generator=g)
+    vals[1] = torch.round(vals[1] * 4) / 4          # heavy ties everywhere, also at the k-th value
+    vals[2, :] = 0.5                                # all equal: the k lowest indices win
+    vals[3, 100:40000] = -7.25                      # clustered top bytes
+    vals[4] = vals[4].abs() * 1e-30                 # tiny positive numbers / denormal range
+    vals[5, 5] = float("inf")
+    v = vals.to(cuda)
+    for k in (1, 100, 256):
+        tv, ti = ops.topk_rows(v, k)
+        rv, _ = torch.topk(v, k, dim=-1)
+        assert torch.equal(tv, rv)                                  # same values, sorted descending
+        assert torch.equal(torch.gather(v, 1, ti), tv)              # indices point at those values
+        assert all(len(set(r.tolist())) == k for r in ti.cpu())     # no duplicates
+        # ties -> lower index first: inside a run of equal values the indices ascend
+        same = tv[:, 1:] == tv[:, :-1]
+        assert bool(((ti[:, 1:] > ti[:, :-1]) | ~same).all())
+    # the selected set under ties is the lowest indices
+    tv, ti = ops.topk_rows(v[2:3], 100)
+    assert ti.cpu().flatten().tolist() == list(range(100))
+
+
+def test_native_head_kernels_match_torch_ops(cuda, no_tf32):
+    """cls logits / top-k / reg gather / decode on the NHWC map vs conv2d + sigmoid + topk + gather (proposal.py:61-78)."""
+    from vision3d_b200 import ops
+    cfg = second.three_class_config()
+    torch.manual_seed(5)
+    head = second.HeadB200(cfg).to(cuda).eval()
+    with torch.no_grad():
+        head.conv_cls.weight.normal_(std=0.05)
+        head.conv_reg.weight.normal_(std=0.05)
+        head.conv_reg.bias.normal_(std=0.1)
+    B, ny, nx, n_cls, n_yaw, K = 2, 200, 176, cfg.NUM_CLASSES, cfg.NUM_YAW, cfg.TOPK
+    fmap = torch.randn((B, 128, ny, nx), device=cuda).contiguous(memory_format=torch.channels_last)
+    anchors = second.make_anchors(cfg).to(cuda)
+    with torch.no_grad():
+        cls_ref = head.conv_cls(fmap).reshape(B, n_cls * n_yaw, -1)
+        reg_ref = head.conv_reg(fmap)
+    w_cls = head.conv_cls.weight.detach().reshape(n_cls * n_yaw, -1).contiguous()
+    logits = ops.head_cls_logits(fmap, w_cls, head.conv_cls.bias.detach())
+    assert torch.allclose(logits, cls_ref, rtol=1e-5, atol=1e-5)
+    top, a_idx = ops.topk_rows(logits.view(B * n_cls, -1), K)
+    N = B * n_cls * K
+    deltas, scores = torch.empty((N, 7), device=cuda), torch.empty(N, device=cuda)
+    w_reg = head.conv_reg.weight.detach().reshape(n_cls * n_yaw * 7, -1).contiguous()
+    ops.head_reg_gather(fmap, w_reg, head.conv_reg.bias.detach(), top, a_idx, n_cls, n_yaw, K, deltas, scores)
+    assert torch.equal(scores, torch.sigmoid(top).reshape(-1))      # same expression as torch.sigmoid
+    # reference gather of the regression map at the same anchors (reshape order of proposal.py:20-26)
+    reg5 = reg_ref.reshape(B, n_cls, 7, n_yaw * ny * nx)
+    want = torch.gather(reg5, 3, a_idx.view(B, n_cls, 1, K).expand(-1, -1, 7, -1)).permute(0, 1, 3, 2).reshape(N, 7)
+    assert torch.allclose(deltas, want, rtol=1e-5, atol=1e-5)
+    boxes, nms_in = torch.empty((N, 7), device=cuda), torch.empty((N, 5), device=cuda)
+    ops.second_head_decode_compact(deltas, anchors, a_idx, B, n_cls, n_yaw, ny, nx, K, boxes, nms_in)
+    b2, n2 = ops.second_head_decode(reg_ref, anchors, a_idx.view(B, n_cls, K).contiguous(), n_cls, n_yaw, K)
+    assert torch.allclose(boxes, b2, rtol=1e-5, atol=1e-5) and torch.allclose(nms_in, n2, rtol=1e-5, atol=1e-3)
+
+
+def test_engine_native_head_vs_torch_head(cuda, no_tf32):
+    cfg = second.car_config()
+    model = second.init_for_benchmark(second.SecondB200(cfg), 2)
+    clouds = synth.make_batch(60, 2, 16384)
+    res = []
+    for fused in (False, True):
+        eng = second.SecondEngine(model, 2, 2 * 16384, cuda, use_graph=fused, fused_head=fused,
+                                  rpn_mode="fused_nhwc").capture()
+        out = eng.infer(clouds)
+        res.append((out, eng._scores.clone().view(2, -1), eng._boxes.clone().view(2, -1, 7)))
+    (o0, s0, b0), (o1, s1, b1) = res
+    assert torch.allclose(s0, s1, rtol=0, atol=2e-6)               # candidate scores, sorted per frame
+    close = torch.isclose(b0, b1, rtol=1e-4, atol=1e-4).all(-1)    # same candidates (order may differ on near ties)
+    assert close.float().mean().item() > 0.97
+    for f in range(2):
+        assert abs(len(o0[f]) - len(o1[f])) <= 1

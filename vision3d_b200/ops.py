@@ -482,3 +482,49 @@ def pack_detections(boxes, scores, keep, count, thr, n_cls, topk, counters_ptrs,
                                               counters_ptrs.data_ptr() if counters_ptrs is not None else None,
                                               int(n_counters), result.data_ptr(), _stream()), "v3d_pack_detections")
     return result
+
+
+def head_cls_logits(fmap, weight, bias, out=None):
+    """fmap (B, 128, ny, nx) in channels_last memory; weight (n_out, 128[,1,1]); -> logits (B, n_out, ny*nx)."""
+    B, C, ny, nx = fmap.shape
+    assert fmap.is_contiguous(memory_format=torch.channels_last) and fmap.dtype == _F32
+    n_out = weight.shape[0]
+    if out is None:
+        out = torch.empty((B, n_out, ny * nx), dtype=_F32, device=fmap.device)
+    with torch.cuda.device(fmap.device):
+        check(_lib.load().v3d_head_cls_logits(fmap.data_ptr(), B, ny * nx, C, weight.data_ptr(),
+                                              bias.data_ptr() if bias is not None else None, n_out, out.data_ptr(),
+                                              _stream()), "v3d_head_cls_logits")
+    return out
+
+
+def topk_rows(values, k, out_values=None, out_index=None):
+    """values (rows, L) f32 -> (top values (rows,k) descending, indices (rows,k) int64); ties -> lower index."""
+    rows, L = values.shape
+    if out_values is None:
+        out_values = torch.empty((rows, k), dtype=_F32, device=values.device)
+    if out_index is None:
+        out_index = torch.empty((rows, k), dtype=torch.int64, device=values.device)
+    with torch.cuda.device(values.device):
+        check(_lib.load().v3d_topk_rows(values.data_ptr(), rows, L, int(k), out_values.data_ptr(),
+                                        out_index.data_ptr(), _stream()), "v3d_topk_rows")
+    return out_values, out_index
+
+
+def head_reg_gather(fmap, w_reg, b_reg, top_logits, anchor_idx, n_cls, n_yaw, topk, deltas, scores):
+    B, C, ny, nx = fmap.shape
+    with torch.cuda.device(fmap.device):
+        check(_lib.load().v3d_head_reg_gather(fmap.data_ptr(), C, w_reg.data_ptr(),
+                                              b_reg.data_ptr() if b_reg is not None else None, top_logits.data_ptr(),
+                                              anchor_idx.data_ptr(), B, int(n_cls), int(n_yaw), ny, nx, int(topk),
+                                              deltas.data_ptr(), scores.data_ptr(), _stream()), "v3d_head_reg_gather")
+    return deltas, scores
+
+
+def second_head_decode_compact(deltas, anchors, anchor_idx, B, n_cls, n_yaw, ny, nx, topk, boxes, nms_in):
+    with torch.cuda.device(deltas.device):
+        check(_lib.load().v3d_second_head_decode_compact(deltas.data_ptr(), anchors.data_ptr(), anchor_idx.data_ptr(),
+                                                         int(B), int(n_cls), int(n_yaw), int(ny), int(nx), int(topk),
+                                                         boxes.data_ptr(), nms_in.data_ptr(), _stream()),
+              "v3d_second_head_decode_compact")
+    return boxes, nms_in

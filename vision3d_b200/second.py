@@ -387,6 +387,18 @@ class SecondEngine:
         self._boxes_buf = torch.empty((self.N, 7), dtype=torch.float32, device=dev)
         self._nms_buf = torch.empty((self.N, 5), dtype=torch.float32, device=dev)
         self._counter_ptrs = torch.tensor([t.data_ptr() for t in self.n_rows], dtype=torch.int64, device=dev)
+        hd = self.model.head
+        n_out = n_cls * cfg.NUM_YAW
+        ny, nx = self.anchors.shape[2], self.anchors.shape[3]
+        self._w_cls = hd.conv_cls.weight.detach().reshape(n_out, -1).contiguous().float()
+        self._b_cls = hd.conv_cls.bias.detach().contiguous().float() if hd.conv_cls.bias is not None else None
+        self._w_reg = hd.conv_reg.weight.detach().reshape(n_out * cfg.BOX_DOF, -1).contiguous().float()
+        self._b_reg = hd.conv_reg.bias.detach().contiguous().float() if hd.conv_reg.bias is not None else None
+        self._logits = torch.empty((B, n_out, ny * nx), dtype=torch.float32, device=dev)
+        self._top_logits = torch.empty((B * n_cls, cfg.TOPK), dtype=torch.float32, device=dev)
+        self._a_idx = torch.zeros((B * n_cls, cfg.TOPK), dtype=torch.int64, device=dev)
+        self._deltas = torch.empty((self.N, 7), dtype=torch.float32, device=dev)
+        self._scores_buf = torch.empty(self.N, dtype=torch.float32, device=dev)
         # ---- RPN (stays cuDNN): "module" = the nn.Sequential as is; "fused" = eval BatchNorm2d folded into
         # the conv weights + cudnn fused conv-bias-ReLU (7 launches instead of 21, no separate BN/ReLU passes
         # over the 288 MB activations); "fused_nhwc" = same in channels_last.
@@ -492,7 +504,9 @@ class SecondEngine:
                 x, self.indices[4], self.n_rows[4], self.caps[4], B, self.shapes[4], self.dense_out,
                 self.dense_ws))))
         plan.append(("rpn(cudnn)", 0, self._rpn))
-        plan.append(("heads+topk(torch)+decode", 1 if self.fused_head else 0, self._head))
+        native_head = self.fused_head and self.rpn_mode == "fused_nhwc"  # logits, top-k, reg gather, decode
+        plan.append(("heads+topk+decode" if native_head else "heads+topk(torch)+decode",
+                     4 if native_head else (1 if self.fused_head else 0), self._head))
         plan.append(("nms_rotated", 3, self._nms))
         plan.append(("pack_result", 1 if self.fused_head else 0, self._pack))
         self.plan = plan
@@ -518,9 +532,23 @@ class SecondEngine:
             self._scores, self._boxes = scores.reshape(-1), boxes.reshape(-1, cfg.BOX_DOF)
             self._nms_in = group_offsets(self._boxes.index_select(1, self.bev_cols), self.g_idx)
             return
-        # 1x1 heads + sigmoid + top-k stay torch/cuDNN; gather + decode + BEV + group offsets = one kernel
         head = self.model.head
         B, n_cls = self.B, cfg.NUM_CLASSES
+        fmap = self._fmap
+        if fmap.is_contiguous(memory_format=torch.channels_last) and fmap.shape[1] == 128 and \
+                n_cls * cfg.NUM_YAW <= 8:
+            # no head maps at all: classification logits in one pass over the NHWC map, top-k on the logits
+            # (sigmoid is monotonic), regression head evaluated only at the top-k anchors, decode
+            ny, nx = fmap.shape[2], fmap.shape[3]
+            ops.head_cls_logits(fmap, self._w_cls, self._b_cls, out=self._logits)
+            ops.topk_rows(self._logits.view(B * n_cls, -1), cfg.TOPK, self._top_logits, self._a_idx)
+            ops.head_reg_gather(fmap, self._w_reg, self._b_reg, self._top_logits, self._a_idx, n_cls, cfg.NUM_YAW,
+                                cfg.TOPK, self._deltas, self._scores_buf)
+            ops.second_head_decode_compact(self._deltas, self.anchors, self._a_idx, B, n_cls, cfg.NUM_YAW, ny, nx,
+                                           cfg.TOPK, self._boxes_buf, self._nms_buf)
+            self._scores, self._boxes, self._nms_in = self._scores_buf, self._boxes_buf, self._nms_buf
+            return
+        # NCHW map: 1x1 heads + sigmoid + top-k stay torch/cuDNN; gather + decode + BEV + group offsets = one kernel
         cls = head.conv_cls(self._fmap).reshape(B, n_cls, -1)  # channel = class * n_yaw + yaw
         reg = head.conv_reg(self._fmap)
         scores, a_idx = cls.sigmoid().topk(cfg.TOPK, -1)
