@@ -201,20 +201,30 @@ __global__ void __launch_bounds__(1024) topk_rows_kernel(const float* __restrict
   for (int shift = 56; shift >= 0; shift -= 8) {
     for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0u;
     __syncthreads();
-    for (int i0 = 0; i0 < L; i0 += blockDim.x) {
-      const int i = i0 + tid;
-      bool in = false;
-      unsigned int digit = 0;
-      if (i < L) {
-        const unsigned long long comp = ((unsigned long long)order_key(__ldg(row + i)) << 32) | (unsigned int)(~i);
-        in = (comp & mask) == prefix;
-        digit = (unsigned int)(comp >> shift) & 255u;
+    constexpr int U = 8;  // loads in flight per thread: one CTA streams its whole row every pass
+    for (int i0 = 0; i0 < L; i0 += U * blockDim.x) {
+      float v[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const int i = i0 + u * blockDim.x + tid;
+        v[u] = i < L ? __ldg(row + i) : 0.f;
       }
-      // warp-aggregated histogram update (values cluster: without it one bin takes tens of thousands of atomics)
-      const unsigned int act = __ballot_sync(0xffffffffu, in);
-      if (in) {
-        const unsigned int peers = __match_any_sync(act, digit);
-        if (lane == (__ffs(peers) - 1)) atomicAdd(&hist[digit], __popc(peers));
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const int i = i0 + u * blockDim.x + tid;
+        bool in = false;
+        unsigned int digit = 0;
+        if (i < L) {
+          const unsigned long long comp = ((unsigned long long)order_key(v[u]) << 32) | (unsigned int)(~i);
+          in = (comp & mask) == prefix;
+          digit = (unsigned int)(comp >> shift) & 255u;
+        }
+        // warp-aggregated histogram update (values cluster: without it one bin takes tens of thousands of atomics)
+        const unsigned int act = __ballot_sync(0xffffffffu, in);
+        if (in) {
+          const unsigned int peers = __match_any_sync(act, digit);
+          if (lane == (__ffs(peers) - 1)) atomicAdd(&hist[digit], __popc(peers));
+        }
       }
     }
     __syncthreads();
@@ -260,11 +270,21 @@ __global__ void __launch_bounds__(1024) topk_rows_kernel(const float* __restrict
   // every composite whose refined digits are >= the boundary's is selected: exactly k of them
   if (tid == 0) s_count = 0u;
   __syncthreads();
-  for (int i = tid; i < L; i += blockDim.x) {
-    const unsigned long long comp = ((unsigned long long)order_key(__ldg(row + i)) << 32) | (unsigned int)(~i);
-    if ((comp & mask) >= prefix) {
-      const unsigned int slot = atomicAdd(&s_count, 1u);
-      if (slot < (unsigned int)kTopkMax) s_pairs[slot] = comp;
+  for (int i0 = 0; i0 < L; i0 += 8 * blockDim.x) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int i = i0 + u * blockDim.x + tid;
+      v[u] = i < L ? __ldg(row + i) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int i = i0 + u * blockDim.x + tid;
+      const unsigned long long comp = ((unsigned long long)order_key(v[u]) << 32) | (unsigned int)(~i);
+      if (i < L && (comp & mask) >= prefix) {
+        const unsigned int slot = atomicAdd(&s_count, 1u);
+        if (slot < (unsigned int)kTopkMax) s_pairs[slot] = comp;
+      }
     }
   }
   __syncthreads();
