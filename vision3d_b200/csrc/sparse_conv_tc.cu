@@ -35,11 +35,9 @@
 // 1024 B apart (SBO); the 16-byte unit u of row r lives at unit u ^ (r & 7). A slot is always K = 64:
 // 64/CIN consecutive kernel offsets are stacked along K. Stage = [A_h1 16 KB | A_h2 16 KB | G1 rows | G2 rows].
 // TMEM columns: two accumulator buffers of 2*COUT columns: [h1*g1 + h2*g1 | h1*g2].
-#include <cuda.h>
 #include <cuda_bf16.h>
 
 #include <cstdlib>
-#include <cstring>
 
 #include "common.cuh"
 
@@ -98,18 +96,6 @@ __device__ __forceinline__ void cp_async16_cg(uint32_t dst, const void* src, uin
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-
-// TMA tile::gather4: four rows (row coordinates r0..r3, out-of-range -> zeros) of a 2-D tensor map, `col` elements
-// in, land as four consecutive 128-byte rows at dst with the map's 128B swizzle applied by the hardware
-__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map, int col, int r0, int r1, int r2, int r3,
-                                            uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
-      : "memory");
-}
-constexpr int kOobRow = 1 << 30;  // row count encoded in the tensor map: every index >= it reads as zeros
 
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -189,11 +175,6 @@ struct TcCfg {
   // pay the per-slot pipeline handshakes once per 64 K-elements instead of once per 16 or 32.
   static constexpr int kGK = 64 / CIN;
   static constexpr int kKSteps = 4;                       // K = 16 per instruction
-  // CIN = 64: a tile row is exactly one packed half-row (128 B), so the gather is done by the TMA unit
-  // (tile::gather4, 64 instructions per slot issued by single lanes) instead of 2048 LDGSTS lanes: the
-  // LDGSTS path keeps the L1TEX data pipe 70 % busy (fills arrive sector by sector: ~7 shared-memory
-  // wavefronts per 512-byte instruction) and caps the kernel at ~940 clk per slot.
-  static constexpr bool kTmaGather = (CIN == 64);
   // B image of one slot: rows [0, COUT) hold G1^T, rows [COUT, 2*COUT) hold G2^T, 128 B per row, so that
   // ONE N = 2*COUT MMA computes A_h1*[G1 | G2] (the gathered operand is fetched once for both products)
   static constexpr int kBBytes = 2 * COUT * 128;
@@ -218,8 +199,7 @@ __global__ void __launch_bounds__(32 * (kWarpFetch0 + kFetchWarps), 1)
 sparse_conv_tc_kernel(const unsigned char* __restrict__ feat, const unsigned char* __restrict__ wprep,
                       const int* __restrict__ nbr, int nbr_stride, const int* __restrict__ n_out_ptr, int out_cap,
                       int KV, const float* __restrict__ scale, const float* __restrict__ shift, int relu,
-                      float* __restrict__ out, unsigned char* __restrict__ out_packed, int bypass_l1,
-                      const __grid_constant__ CUtensorMap feat_map) {
+                      float* __restrict__ out, unsigned char* __restrict__ out_packed, int bypass_l1) {
   using C = TcCfg<CIN, COUT>;
   extern __shared__ unsigned char smem_raw[];
   // round up to 1024 B (SWIZZLE_128B atoms) by OFFSETTING the __shared__ array: casting through an integer
@@ -244,8 +224,7 @@ sparse_conv_tc_kernel(const unsigned char* __restrict__ feat, const unsigned cha
 
   if (tid == 0) {
     for (int s = 0; s < C::kStages; s++) {
-      // LDGSTS path: every fetch thread's copies + the expect_tx arrival (B image); TMA path: that arrival only
-      mbar_init(&full[s], C::kTmaGather ? 1 : kFetchWarps * 32 + 1);
+      mbar_init(&full[s], kFetchWarps * 32 + 1);  // every fetch thread's copies + the expect_tx arrival (B image)
       mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; a++) {
@@ -424,20 +403,8 @@ sparse_conv_tc_kernel(const unsigned char* __restrict__ feat, const unsigned cha
         if (gt == 0) {
           meta[s].last = (mask == 0);
           meta[s].end = 0;
-          mbar_arrive_expect_tx(&full[s], (uint32_t)(C::kBBytes + (C::kTmaGather ? kABytes : 0)));
+          mbar_arrive_expect_tx(&full[s], (uint32_t)C::kBBytes);
           bulk_g2s(smem_u32(ring) + st + kABytes, wprep + (size_t)g * C::kBBytes, (uint32_t)C::kBBytes, &full[s]);
-        }
-        if constexpr (C::kTmaGather) {
-          // lanes 0..63: part = gt & 1 (h1 / h2 half of the packed row), rows 4 (gt >> 1) .. +3 of the tile
-          if (gt < 64) {
-            const int rg = gt >> 1, prt = gt & 1;
-            const int4 r = *reinterpret_cast<const int4*>(idx_tile + g * kTileM + 4 * rg);
-            tma_gather4(smem_u32(ring) + st + (uint32_t)(prt * kATileBytes + rg * 512), &feat_map, prt * 64,
-                        r.x >= 0 ? r.x : kOobRow, r.y >= 0 ? r.y : kOobRow, r.z >= 0 ? r.z : kOobRow,
-                        r.w >= 0 ? r.w : kOobRow, &full[s]);
-          }
-          q++;
-          continue;
         }
         const int kk = g * C::kGK + off;
         const bool kv_ok = kk < KV;  // the last group of a layer may be padded with non-existent offsets
@@ -466,7 +433,7 @@ sparse_conv_tc_kernel(const unsigned char* __restrict__ feat, const unsigned cha
         meta[s].end = 1;
         mbar_arrive(&full[s]);  // stands in for the expect_tx arrival of a real slot
       }
-      if (!C::kTmaGather) mbar_arrive(&full[s]);
+      mbar_arrive(&full[s]);
     }
   }
 
@@ -526,29 +493,6 @@ __global__ void feature_pack_kernel(const float* __restrict__ feat, const int* _
   }
 }
 
-// 2-D tensor map over packed rows (2*C bf16 per row) for tile::gather4: box = one 128-byte half-row, 128B swizzle.
-// The driver entry point is resolved through the runtime (no link-time dependency on libcuda).
-inline int encode_feature_map(CUtensorMap* map, const unsigned char* feat, int C) {
-  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  static EncodeFn encode = nullptr;
-  if (!encode) {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    V3D_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-    if (!fn || qres != cudaDriverEntryPointSuccess) return V3D_ERR_CUDA;
-    encode = reinterpret_cast<EncodeFn>(fn);
-  }
-  const cuuint64_t dims[2] = {(cuuint64_t)(2 * C), (cuuint64_t)kOobRow};
-  const cuuint64_t strides[1] = {(cuuint64_t)(4 * C)};  // bytes between rows
-  const cuuint32_t box[2] = {64u, 1u}, estr[2] = {1u, 1u};
-  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<unsigned char*>(feat), dims, strides, box,
-                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? V3D_OK : V3D_ERR_CUDA;
-}
-
 template <int CIN, int COUT>
 int launch_tc(const unsigned char* feat, const unsigned char* wprep, const int* nbr, int nbr_stride, const int* n_out,
               int out_cap, int KV, const float* scale, const float* shift, int relu, float* out,
@@ -569,15 +513,9 @@ int launch_tc(const unsigned char* feat, const unsigned char* wprep, const int* 
   }
   const int tiles_cap = ceil_div(out_cap, kTileM);
   const int grid = tiles_cap < kNumSMs ? (tiles_cap > 0 ? tiles_cap : 1) : kNumSMs;
-  CUtensorMap fmap;
-  memset(&fmap, 0, sizeof(fmap));
-  if (C::kTmaGather) {
-    const int rc = encode_feature_map(&fmap, feat, CIN);
-    if (rc != V3D_OK) return rc;
-  }
 #define V3D_TC_LAUNCH(FW)                                                                                          \
   sparse_conv_tc_kernel<CIN, COUT, FW><<<grid, 32 * (kWarpFetch0 + FW), C::kSmemBytes, st>>>(                      \
-      feat, wprep, nbr, nbr_stride, n_out, out_cap, KV, scale, shift, relu, out, out_packed, bypass_l1, fmap)
+      feat, wprep, nbr, nbr_stride, n_out, out_cap, KV, scale, shift, relu, out, out_packed, bypass_l1)
   if (fetch_warps == 4) V3D_TC_LAUNCH(4);
   else if (fetch_warps == 16) V3D_TC_LAUNCH(16);
   else V3D_TC_LAUNCH(8);
