@@ -79,6 +79,14 @@ V3D_API size_t v3d_nms_rotated_workspace_bytes(int N);
 V3D_API int v3d_nms_rotated(const float* dets, const float* scores, int N, float iou_threshold,
                             int64_t* keep, int* num_keep, void* workspace, size_t workspace_bytes,
                             v3d_stream_t stream);
+/* Same result for inputs that are consecutive groups of `group_size` (<= 128) boxes which cannot overlap across
+ * groups -- what batched_nms_rotated's per-group coordinate offsets (ops/iou_nms.py:121-132) build before it
+ * calls nms_rotated: cross-group IoU is exactly 0, so the greedy NMS decomposes into one per group (same
+ * comparator, same IoU arithmetic on the same offset coordinates). One CTA per group instead of an N x N mask.
+ * The caller guarantees the disjointness; same workspace as v3d_nms_rotated. */
+V3D_API int v3d_nms_rotated_grouped(const float* dets, const float* scores, int N, int group_size,
+                                    float iou_threshold, int64_t* keep, int* num_keep, void* workspace,
+                                    size_t workspace_bytes, v3d_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a1 (+a2)  point -> voxel for a whole batch in one call

@@ -515,3 +515,27 @@ def test_voxelize_cluster_dsmem_variant_subprocess(cuda):
     env = dict(os.environ, V3D_VOXELIZE_CLUSTER="1")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert "cluster-ok" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
+
+
+def test_grouped_nms_equals_global_nms_on_offset_groups(cuda):
+    """v3d_nms_rotated_grouped == v3d_nms_rotated == oracle on groups separated by the batched_nms offsets."""
+    from vision3d_b200 import ops
+    rng = np.random.default_rng(17)
+    for gs, ng in ((100, 16), (128, 3), (37, 5), (1, 4)):
+        n = gs * ng
+        ctr = rng.uniform(0, 40, (n, 2))
+        wl = rng.uniform(1.0, 6.0, (n, 2))
+        ang = rng.uniform(-180, 180, (n, 1))
+        boxes = np.concatenate([ctr, wl, ang], 1).astype(np.float32)
+        scores = rng.random(n).astype(np.float32)
+        scores[rng.integers(0, n, n // 5)] = 0.5                      # ties -> lower index first
+        grp = np.repeat(np.arange(ng), gs).astype(np.float32)
+        span = np.float32(boxes[:, :2].max() + boxes[:, 2:4].max() / 2 - (boxes[:, :2].min() - boxes[:, 2:4].min() / 2) + 1)
+        off = boxes.copy()
+        off[:, :2] += (grp * span)[:, None]                           # ops/iou_nms.py:121-132
+        d, s = _t(off, cuda), _t(scores, cuda)
+        k0, c0 = ops.nms_rotated_padded(d, s, 0.01)
+        k1, c1 = ops.nms_rotated_padded(d, s, 0.01, group_size=gs)
+        n0, n1 = int(c0.item()), int(c1.item())
+        assert n0 == n1 and torch.equal(k0[:n0], k1[:n1])
+        assert np.array_equal(k1[:n1].cpu().numpy(), oracle.nms_rotated(off, scores, 0.01, 1))

@@ -401,6 +401,71 @@ __global__ void __launch_bounds__(1024) nms_scan_kernel(const unsigned long long
   if (tid == 0) *num_keep = kept_base;
 }
 
+// -------------------------------------------------------------------------------------------
+// Grouped NMS: the N boxes are G consecutive groups of `gs` boxes that cannot overlap ACROSS groups -- exactly
+// what batched_nms_rotated's per-group coordinate offsets (ops/iou_nms.py:121-132) construct before calling
+// nms_rotated. Cross-group IoU is then exactly 0, so the global greedy NMS decomposes into one independent
+// greedy NMS per group with the same comparator (score descending, ties -> lower index) and the same IoU
+// arithmetic on the same (offset) coordinates: identical keep set, identical order. One CTA per group: counting
+// rank + invariants, upper-triangular pair tests into a shared-memory bit matrix, 1-thread greedy chain.
+// A tiny second kernel compacts the survivors in GLOBAL score order.
+// -------------------------------------------------------------------------------------------
+constexpr int kGroupMax = 128;
+
+__global__ void __launch_bounds__(1024) nms_group_kernel(const float* __restrict__ dets, const float* __restrict__ scores,
+                                                         int N, int gs, float thr, unsigned char* __restrict__ kept) {
+  __shared__ BoxPre pre[kGroupMax];
+  __shared__ float sc[kGroupMax];
+  __shared__ int ord[kGroupMax];
+  __shared__ unsigned long long bits[kGroupMax][2];
+  const int g0 = blockIdx.x * gs, n = min(gs, N - g0), tid = threadIdx.x;
+  if (tid < n) sc[tid] = rank_key(__ldg(&scores[g0 + tid]));
+  if (tid < kGroupMax) bits[tid][0] = bits[tid][1] = 0ull;
+  __syncthreads();
+  if (tid < n) {
+    const float si = sc[tid];
+    int cnt = 0;
+    for (int j = 0; j < n; j++) cnt += (sc[j] > si) || (sc[j] == si && j < tid);
+    ord[cnt] = tid;
+    pre[cnt] = make_pre(dets + (size_t)(g0 + tid) * 5);
+  }
+  __syncthreads();
+  for (int p = tid; p < n * n; p += blockDim.x) {
+    const int r = p / n, c = p - r * n;
+    if (c > r && iou_pair(pre[r], pre[c]) > thr) atomicOr(&bits[r][c >> 6], 1ull << (c & 63));  // nms_rotated_cuda.cu:62-63
+  }
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long rem0 = 0ull, rem1 = 0ull;
+    for (int r = 0; r < n; r++) {
+      const bool dead = r < 64 ? ((rem0 >> r) & 1ull) : ((rem1 >> (r - 64)) & 1ull);
+      kept[g0 + ord[r]] = dead ? 0 : 1;
+      if (!dead) {
+        rem0 |= bits[r][0];
+        rem1 |= bits[r][1];
+      }
+    }
+  }
+}
+
+// survivors in global descending-score order (order[] from nms_rank_kernel)
+__global__ void __launch_bounds__(1024) nms_compact_kernel(const int* __restrict__ order, const unsigned char* __restrict__ kept,
+                                                           int N, long long* __restrict__ keep, int* __restrict__ num_keep) {
+  __shared__ int sm[33];
+  int base = 0;
+  for (int r0 = 0; r0 < N; r0 += blockDim.x) {
+    const int r = r0 + threadIdx.x;
+    const int i = r < N ? order[r] : 0;
+    const int flag = (r < N && kept[i]) ? 1 : 0;
+    int total;
+    const int ex = block_exclusive_scan(flag, sm, total);
+    if (flag) keep[base + ex] = (long long)i;
+    base += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *num_keep = base;
+}
+
 struct NmsLayout {
   size_t order_off, pre_off, mask_off, total;
 };
@@ -433,6 +498,28 @@ extern "C" int v3d_box_iou_rotated(const float* boxes1, int M, const float* boxe
 extern "C" size_t v3d_nms_rotated_workspace_bytes(int N) {
   if (N <= 0) return 256;
   return nms_layout(N).total;
+}
+
+extern "C" int v3d_nms_rotated_grouped(const float* dets, const float* scores, int N, int group_size,
+                                       float iou_threshold, int64_t* keep, int* num_keep, void* workspace,
+                                       size_t workspace_bytes, v3d_stream_t stream) {
+  if (N < 0 || !num_keep || group_size <= 0 || group_size > kGroupMax) return V3D_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = as_stream(stream);
+  if (N == 0) {
+    V3D_CUDA_TRY(cudaMemsetAsync(num_keep, 0, sizeof(int), st));
+    return V3D_OK;
+  }
+  if (!dets || !scores || !keep || !workspace || N > 65536) return V3D_ERR_INVALID_ARGUMENT;
+  NmsLayout l = nms_layout(N);
+  if (workspace_bytes < l.total) return V3D_ERR_WORKSPACE_TOO_SMALL;
+  char* ws = static_cast<char*>(workspace);
+  int* order = reinterpret_cast<int*>(ws + l.order_off);
+  BoxPre* pre = reinterpret_cast<BoxPre*>(ws + l.pre_off);
+  unsigned char* kept = reinterpret_cast<unsigned char*>(ws + l.mask_off);  // N bytes of the mask area
+  nms_rank_kernel<<<ceil_div(N, 8), 256, 0, st>>>(dets, scores, N, order, pre);
+  nms_group_kernel<<<ceil_div(N, group_size), 1024, 0, st>>>(dets, scores, N, group_size, iou_threshold, kept);
+  nms_compact_kernel<<<1, 1024, 0, st>>>(order, kept, N, reinterpret_cast<long long*>(keep), num_keep);
+  return check_launch();
 }
 
 extern "C" int v3d_nms_rotated(const float* dets, const float* scores, int N, float iou_threshold,

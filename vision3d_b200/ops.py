@@ -73,8 +73,9 @@ def nms_workspace(n, device):
     return torch.empty(nbytes, dtype=torch.uint8, device=device)
 
 
-def nms_rotated_padded(dets, scores, iou_threshold, workspace=None, keep=None, count=None):
-    """No host sync. Returns (keep[N] int64, count[1] int32); keep[:count] is valid."""
+def nms_rotated_padded(dets, scores, iou_threshold, workspace=None, keep=None, count=None, group_size=None):
+    """No host sync. Returns (keep[N] int64, count[1] int32); keep[:count] is valid. `group_size`: the boxes are
+    consecutive groups of that many boxes that cannot overlap across groups (batched_nms_rotated's offsets)."""
     d = _cuda_f32(dets, "dets", 5)
     s = _cuda_f32(scores, "scores")
     n = d.shape[0]
@@ -87,6 +88,12 @@ def nms_rotated_padded(dets, scores, iou_threshold, workspace=None, keep=None, c
     if workspace is None:
         workspace = nms_workspace(n, d.device)
     with torch.cuda.device(d.device):
+        if group_size:
+            check(_lib.load().v3d_nms_rotated_grouped(d.data_ptr(), s.data_ptr(), n, int(group_size),
+                                                      float(iou_threshold), keep.data_ptr(), count.data_ptr(),
+                                                      workspace.data_ptr(), workspace.numel(), _stream()),
+                  "v3d_nms_rotated_grouped")
+            return keep, count
         check(_lib.load().v3d_nms_rotated(d.data_ptr(), s.data_ptr(), n, float(iou_threshold), keep.data_ptr(),
                                           count.data_ptr(), workspace.data_ptr(), workspace.numel(), _stream()),
               "v3d_nms_rotated")

@@ -299,8 +299,9 @@ def _fold_bn(bn):
 class SecondEngine:
     def __init__(self, model: SecondB200, batch_size: int, points_capacity: int, device, level_caps=None,
                  use_graph=True, cap_policy=0, frame_points_capacity=None, tensor_cores=True, rpn_mode="fused",
-                 fused_head=True):
+                 fused_head=True, grouped_nms=True):
         cfg = model.cfg
+        self.grouped_nms = bool(grouped_nms)
         self.cfg, self.B, self.P = cfg, int(batch_size), int(points_capacity)
         self.dev = torch.device(device)
         self.model = model.to(self.dev).eval()
@@ -559,7 +560,11 @@ class SecondEngine:
 
     def _nms(self):
         self.keep.zero_()
-        ops.nms_rotated_padded(self._nms_in, self._scores, self.cfg.NMS_THRESH, self.nms_ws, self.keep, self.count)
+        # candidates are laid out (frame, class, k): TOPK consecutive boxes per group, groups separated by the
+        # coordinate offsets -> one CTA per group instead of the N x N mask (bit-identical keep list)
+        gs = self.cfg.TOPK if (self.grouped_nms and self.cfg.TOPK <= 128) else None
+        ops.nms_rotated_padded(self._nms_in, self._scores, self.cfg.NMS_THRESH, self.nms_ws, self.keep, self.count,
+                               group_size=gs)
 
     def _pack(self):
         if self.fused_head:
