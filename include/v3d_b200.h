@@ -197,7 +197,9 @@ V3D_API int v3d_sparse_conv_fwd(const float* feat, const float* weight, const in
 V3D_API size_t v3d_sparse_conv_prepared_bytes(int kernel_volume, int Cin, int Cout);
 V3D_API int v3d_sparse_conv_prepare(const float* weight, int kernel_volume, int Cin, int Cout, void* prepared,
                                     size_t prepared_bytes, v3d_stream_t stream);
-V3D_API int v3d_feature_pack(const float* feat, const int* n_rows, int capacity_rows, int C, void* packed,
+/* feat (rows, C_src) f32 -> packed (rows, 2*C) bf16, channels C_src..C-1 zero (C_src <= C, C_src % 4 == 0): a
+ * narrow input (the 4-channel voxel means) is padded to the 16 channels the tensor-core path needs */
+V3D_API int v3d_feature_pack(const float* feat, const int* n_rows, int capacity_rows, int C_src, int C, void* packed,
                              v3d_stream_t stream);
 V3D_API int v3d_sparse_conv_fwd_tc(const void* feat_packed, const void* prepared, const int* nbr, int nbr_stride,
                                    const int* n_out, int out_capacity, int kernel_volume, int Cin, int Cout,

@@ -41,7 +41,7 @@ SIGNATURES = {
     "v3d_sparse_conv_fwd": (c_int, [P, P, P, c_int, P, c_int, c_int, c_int, c_int, P, P, c_int, P, P]),
     "v3d_sparse_conv_prepared_bytes": (c_size_t, [c_int, c_int, c_int]),
     "v3d_sparse_conv_prepare": (c_int, [P, c_int, c_int, c_int, P, c_size_t, P]),
-    "v3d_feature_pack": (c_int, [P, P, c_int, c_int, P, P]),
+    "v3d_feature_pack": (c_int, [P, P, c_int, c_int, c_int, P, P]),
     "v3d_sparse_conv_fwd_tc": (c_int, [P, P, P, c_int, P, c_int, c_int, c_int, c_int, P, P, c_int, P, P, P]),
     "v3d_sparse_to_dense_workspace_bytes": (c_size_t, [c_int, P]),
     "v3d_sparse_to_dense": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P, c_size_t, P]),

@@ -78,8 +78,10 @@ struct ConvGeom {
 // in set, stride 1, pad k/2) and by the strided conv once its output rows are known.
 __global__ void __launch_bounds__(256) rule_lookup_kernel(SiteTable T, const int4* __restrict__ out_idx,
                                                           const int* __restrict__ n_out, int out_cap,
-                                                          ConvGeom G, int identity_kk,
+                                                          ConvGeom G, int identity_kk, int mirror_kv,
                                                           int* __restrict__ nbr, int nbr_stride) {
+  // mirror_kv = KV for SubM (else 0): nbr[kk][o] = r  <=>  nbr[KV-1-kk][r] = o, so only the offsets below the
+  // centre are looked up and each hit also writes its mirror entry (the upper half is pre-filled with -1)
   const int n = min(*n_out, out_cap);
   const unsigned int calls = T.hdr->epoch;
   const unsigned int epoch = epoch24(calls);
@@ -96,6 +98,7 @@ __global__ void __launch_bounds__(256) rule_lookup_kernel(SiteTable T, const int
         const bool zy_ok = z >= 0 && z < G.in_shape[0] && y >= 0 && y < G.in_shape[1];
         for (int kx = 0; kx < G.ks[2]; kx++, kk++) {
           int r;
+          if (mirror_kv && kk > identity_kk) continue;
           if (kk == identity_kk) {
             r = o;
           } else {
@@ -108,6 +111,7 @@ __global__ void __launch_bounds__(256) rule_lookup_kernel(SiteTable T, const int
                 if ((unsigned int)(v >> 32) == calls) r = (int)(unsigned int)v;  // else: stale alias, not a site
               }
             }
+            if (mirror_kv && r >= 0) nbr[(size_t)(mirror_kv - 1 - kk) * nbr_stride + r] = o;
           }
           nbr[(size_t)kk * nbr_stride + o] = r;
         }
@@ -275,7 +279,7 @@ __global__ void __launch_bounds__(256) conv_rank_kernel(ConvWs W, ConvGeom G, in
 // word per candidate, and only for present neighbours one prefix pair + <= 1 sector of popcounts).
 __global__ void __launch_bounds__(256) rule_lookup_rank_kernel(ConvWs Win, const int4* __restrict__ out_idx,
                                                                const int* __restrict__ n_out, int out_cap,
-                                                               ConvGeom G, int identity_kk,
+                                                               ConvGeom G, int identity_kk, int mirror_kv,
                                                                int* __restrict__ nbr, int nbr_stride) {
   const int n = min(*n_out, out_cap);
   // one thread per output row walks all kernel offsets: the row's coordinates are loaded once, neighbours
@@ -292,11 +296,13 @@ __global__ void __launch_bounds__(256) rule_lookup_rank_kernel(ConvWs Win, const
         const size_t row_base = (((size_t)c.x * G.in_shape[0] + z) * G.in_shape[1] + y) * G.in_shape[2];
         for (int kx = 0; kx < G.ks[2]; kx++, kk++) {
           int r;
+          if (mirror_kv && kk > identity_kk) continue;  // written by the mirror of an offset below the centre
           if (kk == identity_kk) {
             r = o;
           } else {
             const int x = c.w * G.stride[2] - G.pad[2] + kx * G.dil[2];
             r = (zy_ok && x >= 0 && x < G.in_shape[2]) ? rank_of_cell(Win, (unsigned int)(row_base + x)) : -1;
+            if (mirror_kv && r >= 0) nbr[(size_t)(mirror_kv - 1 - kk) * nbr_stride + r] = o;
           }
           nbr[(size_t)kk * nbr_stride + o] = r;
         }
@@ -371,8 +377,11 @@ extern "C" int v3d_rulebook_subm(const void* table, const int* indices, const in
   const int centre = ((ksize_host[0] / 2) * ksize_host[1] + ksize_host[1] / 2) * ksize_host[2] +
                      ksize_host[2] / 2;
   dim3 grid(row_grid(capacity_rows));
+  // entries above the centre offset are produced as mirrors of the ones below it: pre-fill them with -1
+  V3D_CUDA_TRY(cudaMemsetAsync(nbr + (size_t)(centre + 1) * nbr_stride, 0xFF,
+                               sizeof(int) * (size_t)(G.KV - 1 - centre) * nbr_stride, as_stream(stream)));
   rule_lookup_kernel<<<grid, 256, 0, as_stream(stream)>>>(T, reinterpret_cast<const int4*>(indices), n_rows,
-                                                          capacity_rows, G, centre, nbr, nbr_stride);
+                                                          capacity_rows, G, centre, G.KV, nbr, nbr_stride);
   return check_launch();
 }
 
@@ -395,8 +404,10 @@ extern "C" int v3d_rulebook_subm_ranked(const void* level_index, int B, int inde
   const unsigned long long cells = (unsigned long long)B * shape_host[0] * shape_host[1] * shape_host[2];
   ConvWs Win = conv_layout(const_cast<void*>(level_index), cells, index_capacity);
   const int centre = ((ksize_host[0] / 2) * ksize_host[1] + ksize_host[1] / 2) * ksize_host[2] + ksize_host[2] / 2;
+  V3D_CUDA_TRY(cudaMemsetAsync(nbr + (size_t)(centre + 1) * nbr_stride, 0xFF,
+                               sizeof(int) * (size_t)(G.KV - 1 - centre) * nbr_stride, as_stream(stream)));
   rule_lookup_rank_kernel<<<dim3(row_grid(capacity_rows)), 256, 0, as_stream(stream)>>>(
-      Win, reinterpret_cast<const int4*>(indices), n_rows, capacity_rows, G, centre, nbr, nbr_stride);
+      Win, reinterpret_cast<const int4*>(indices), n_rows, capacity_rows, G, centre, G.KV, nbr, nbr_stride);
   return check_launch();
 }
 
@@ -446,11 +457,11 @@ static int rulebook_conv_impl(const void* in_table, const void* in_level_index, 
     const unsigned long long in_cells = (unsigned long long)B * shape_host[0] * shape_host[1] * shape_host[2];
     ConvWs Win = conv_layout(const_cast<void*>(in_level_index), in_cells, in_index_capacity);
     rule_lookup_rank_kernel<<<dim3(row_grid(out_capacity)), 256, 0, st>>>(
-        Win, reinterpret_cast<const int4*>(out_indices), n_out, out_capacity, G, -1, nbr, nbr_stride);
+        Win, reinterpret_cast<const int4*>(out_indices), n_out, out_capacity, G, -1, 0, nbr, nbr_stride);
   } else {
     SiteTable T = table_layout(const_cast<void*>(in_table), capacity_rows);
     rule_lookup_kernel<<<dim3(row_grid(out_capacity)), 256, 0, st>>>(
-        T, reinterpret_cast<const int4*>(out_indices), n_out, out_capacity, G, -1, nbr, nbr_stride);
+        T, reinterpret_cast<const int4*>(out_indices), n_out, out_capacity, G, -1, 0, nbr, nbr_stride);
   }
   return check_launch();
 }

@@ -471,17 +471,19 @@ __global__ void prepare_weights_kernel(const float* __restrict__ w, int KV, int 
   }
 }
 
-// fp32 feature rows -> packed rows [h1 | h2] (one thread per 8 channels)
-__global__ void feature_pack_kernel(const float* __restrict__ feat, const int* __restrict__ n_rows_ptr, int cap, int C,
-                                    unsigned char* __restrict__ packed) {
+// fp32 feature rows (Csrc channels) -> packed rows [h1 | h2] of C >= Csrc channels, zero padded (one thread per
+// 8 output channels). Padding lets narrow inputs (the 4-channel voxel means) use the K = 16 tensor-core path.
+__global__ void feature_pack_kernel(const float* __restrict__ feat, const int* __restrict__ n_rows_ptr, int cap, int Csrc,
+                                    int C, unsigned char* __restrict__ packed) {
   const int n_rows = min(*n_rows_ptr, cap);
   const int upr = C / 8;
   const long long total = (long long)n_rows * upr;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const long long r = e / upr;
-    const int u = (int)(e % upr);
-    const float4 a = __ldg(reinterpret_cast<const float4*>(feat + r * C + u * 8));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(feat + r * C + u * 8 + 4));
+    const int u = (int)(e % upr), c0 = u * 8;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (c0 < Csrc) a = __ldg(reinterpret_cast<const float4*>(feat + r * Csrc + c0));
+    if (c0 + 4 < Csrc) b = __ldg(reinterpret_cast<const float4*>(feat + r * Csrc + c0 + 4));
     uint32_t h1[4], h2[4];
     split2(a.x, a.y, h1[0], h2[0]);
     split2(a.z, a.w, h1[1], h2[1]);
@@ -550,15 +552,17 @@ extern "C" int v3d_sparse_conv_prepare(const float* weight, int kernel_volume, i
   return check_launch();
 }
 
-extern "C" int v3d_feature_pack(const float* feat, const int* n_rows, int capacity, int C, void* packed,
+extern "C" int v3d_feature_pack(const float* feat, const int* n_rows, int capacity, int C_src, int C, void* packed,
                                 v3d_stream_t stream) {
   if (!feat || !n_rows || !packed || capacity <= 0) return V3D_ERR_INVALID_ARGUMENT;
   if (C != 16 && C != 32 && C != 64) return V3D_ERR_INVALID_ARGUMENT;
+  if (C_src <= 0 || C_src > C || (C_src & 3)) return V3D_ERR_INVALID_ARGUMENT;
   if ((reinterpret_cast<uintptr_t>(feat) & 15) || (reinterpret_cast<uintptr_t>(packed) & 15)) return V3D_ERR_INVALID_ARGUMENT;
   const long long units = (long long)capacity * (C / 8);
   const long long want = (units + 255) / 256, cap_blocks = (long long)kNumSMs * 8;
   const int blocks = (int)(want < cap_blocks ? want : cap_blocks);
-  feature_pack_kernel<<<blocks, 256, 0, as_stream(stream)>>>(feat, n_rows, capacity, C, static_cast<unsigned char*>(packed));
+  feature_pack_kernel<<<blocks, 256, 0, as_stream(stream)>>>(feat, n_rows, capacity, C_src, C,
+                                                             static_cast<unsigned char*>(packed));
   return check_launch();
 }
 

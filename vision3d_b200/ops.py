@@ -293,15 +293,16 @@ def _rows_of(feat, n_out, nbr):
     return torch.full((1,), feat.shape[0], dtype=torch.int32, device=feat.device)
 
 
-def pack_features(feat, n_rows, out=None):
-    """fp32 rows (cap, C) -> packed rows (cap, 2*C) bf16 = [h1 | h2] with h1 = bf16(x), h2 = bf16(x - h1):
-    the operand format of the tensor-core sparse conv (v3d_feature_pack)."""
-    cap, c = feat.shape
+def pack_features(feat, n_rows, out=None, channels=None):
+    """fp32 rows (cap, Csrc) -> packed rows (cap, 2*C) bf16 = [h1 | h2] with h1 = bf16(x), h2 = bf16(x - h1):
+    the operand format of the tensor-core sparse conv (v3d_feature_pack). `channels` = C >= Csrc zero-pads."""
+    cap, csrc = feat.shape
+    c = int(channels or csrc)
     if out is None:
         out = torch.empty((cap, 2 * c), dtype=torch.bfloat16, device=feat.device)
     assert out.shape == (cap, 2 * c) and out.dtype == torch.bfloat16 and feat.dtype == _F32
     with torch.cuda.device(feat.device):
-        check(_lib.load().v3d_feature_pack(feat.data_ptr(), n_rows.data_ptr(), int(cap), int(c), out.data_ptr(),
+        check(_lib.load().v3d_feature_pack(feat.data_ptr(), n_rows.data_ptr(), int(cap), int(csrc), c, out.data_ptr(),
                                            _stream()), "v3d_feature_pack")
     return out
 

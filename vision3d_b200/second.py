@@ -335,7 +335,9 @@ class SecondEngine:
                 conv, bn = seq[0], seq[1]
                 scale, shift = _fold_bn(bn)
                 w = conv.weight.detach().reshape(-1, conv.in_channels, conv.out_channels).contiguous().float()
-                if tensor_cores:  # tcgen05 3xTF32 path where the shape supports it (Cin >= 16), else exact fp32
+                if tensor_cores:  # tcgen05 bf16x3 path; a narrow input (the 4-channel voxel means) is zero padded
+                    if w.shape[1] < 16 and w.shape[1] % 4 == 0:  # to the 16 channels one K step needs
+                        w = torch.nn.functional.pad(w, (0, 0, 0, 16 - w.shape[1]))
                     w = ops.PreparedWeights(w)
                 d = dict(kind=l[0], w=w, scale=scale, shift=shift, cin=conv.in_channels, cout=conv.out_channels,
                          level_in=b, ks=conv.kernel_size, stride=conv.stride, pad=conv.padding, dil=conv.dilation)
@@ -467,10 +469,11 @@ class SecondEngine:
                     plan.append((name, 1, (lambda: ops.sparse_conv(x, d["w"], nbr, n_rows_out, cap_out, d["scale"],
                                                                     d["shift"], True, out=out32))))
                     return out32
-                if x.dtype != torch.bfloat16:  # fp32 rows from the SIMT layer -> packed operand format
-                    xp = self.featp[lv][2]
+                if x.dtype != torch.bfloat16:  # fp32 rows (voxel means) -> packed operand format
+                    xp = self.featp[lv][2][:, :2 * d["w"].cin]
+                    assert xp.is_contiguous()
                     plan.append(("pack_L%d" % lv, 1, (lambda x=x, xp=xp, lv=lv: ops.pack_features(
-                        x, self.n_rows[lv], out=xp))))
+                        x, self.n_rows[lv], out=xp, channels=xp.shape[1] // 2))))
                     x = xp
                 outp = self.featp[lv_out][buf]
                 assert outp.data_ptr() != x.data_ptr()
