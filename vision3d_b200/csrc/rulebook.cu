@@ -274,37 +274,6 @@ __global__ void __launch_bounds__(256) conv_rank_kernel(ConvWs W, ConvGeom G, in
   }
 }
 
-// Strided-conv rule table from the INPUT side: every input row reaches at most prod(ceil(k/stride)) output
-// cells (3.4 on average for k=3, s=2), whose row numbers come from the just-built bitmap/prefix index, so the
-// table costs ~3 rank lookups per input row instead of KV index probes per output row (11.5 M hash probes for
-// level 0 -> 0.8 M rank lookups). nbr is pre-filled with -1.
-__global__ void __launch_bounds__(256) conv_scatter_kernel(const int4* __restrict__ idx, const int* __restrict__ n_rows,
-                                                           int cap_rows, ConvGeom G, ConvWs W, int out_capacity,
-                                                           int* __restrict__ nbr, int nbr_stride) {
-  const int n = min(*n_rows, cap_rows);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int4 c = idx[i];
-    for (int kz = 0; kz < G.ks[0]; kz++) {
-      const int nz = c.y + G.pad[0] - kz * G.dil[0];
-      const int oz = nz / G.stride[0];
-      if (nz < 0 || (nz - oz * G.stride[0]) != 0 || oz >= G.out_shape[0]) continue;
-      for (int ky = 0; ky < G.ks[1]; ky++) {
-        const int ny = c.z + G.pad[1] - ky * G.dil[1];
-        const int oy = ny / G.stride[1];
-        if (ny < 0 || (ny - oy * G.stride[1]) != 0 || oy >= G.out_shape[1]) continue;
-        const size_t row_base = (((size_t)c.x * G.out_shape[0] + oz) * G.out_shape[1] + oy) * G.out_shape[2];
-        for (int kx = 0; kx < G.ks[2]; kx++) {
-          const int nx = c.w + G.pad[2] - kx * G.dil[2];
-          const int ox = nx / G.stride[2];
-          if (nx < 0 || (nx - ox * G.stride[2]) != 0 || ox >= G.out_shape[2]) continue;
-          const int o = rank_of_cell(W, (unsigned int)(row_base + ox));
-          if (o >= 0 && o < out_capacity) nbr[(size_t)((kz * G.ks[1] + ky) * G.ks[2] + kx) * nbr_stride + o] = i;
-        }
-      }
-    }
-  }
-}
-
 // Same contract as rule_lookup_kernel, for an INPUT level whose rows are in ascending flat order and
 // indexed by the bitmap/prefix workspace of the strided conv that produced it (no hash probes: one bitmap
 // word per candidate, and only for present neighbours one prefix pair + <= 1 sector of popcounts).
@@ -484,13 +453,16 @@ static int rulebook_conv_impl(const void* in_table, const void* in_level_index, 
   conv_scan_l2_kernel<<<1, 1024, 0, st>>>(W, n_out);
   conv_rank_kernel<<<row_grid((int)(W.n_words < (1u << 30) ? W.n_words : (1u << 30))), 256, 0, st>>>(W, G, out_capacity,
                                                           reinterpret_cast<int4*>(out_indices));
-  // rule table from the input side (the input level's own index is not needed any more)
-  (void)in_table;
-  (void)in_level_index;
-  (void)in_index_capacity;
-  V3D_CUDA_TRY(cudaMemsetAsync(nbr, 0xFF, sizeof(int) * (size_t)G.KV * nbr_stride, st));
-  conv_scatter_kernel<<<dim3(row_grid(capacity_rows)), 256, 0, st>>>(reinterpret_cast<const int4*>(indices), n_rows,
-                                                                     capacity_rows, G, W, out_capacity, nbr, nbr_stride);
+  if (in_level_index) {
+    const unsigned long long in_cells = (unsigned long long)B * shape_host[0] * shape_host[1] * shape_host[2];
+    ConvWs Win = conv_layout(const_cast<void*>(in_level_index), in_cells, in_index_capacity);
+    rule_lookup_rank_kernel<<<dim3(row_grid(out_capacity)), 256, 0, st>>>(
+        Win, reinterpret_cast<const int4*>(out_indices), n_out, out_capacity, G, -1, 0, nbr, nbr_stride);
+  } else {
+    SiteTable T = table_layout(const_cast<void*>(in_table), capacity_rows);
+    rule_lookup_kernel<<<dim3(row_grid(out_capacity)), 256, 0, st>>>(
+        T, reinterpret_cast<const int4*>(out_indices), n_out, out_capacity, G, -1, 0, nbr, nbr_stride);
+  }
   return check_launch();
 }
 
