@@ -411,28 +411,59 @@ __global__ void __launch_bounds__(1024) nms_scan_kernel(const unsigned long long
 // A tiny second kernel compacts the survivors in GLOBAL score order.
 // -------------------------------------------------------------------------------------------
 constexpr int kGroupMax = 128;
+constexpr int kGroupSlices = 8;  // CTAs per group for the pair tests (rows r = slice, slice + 8, ...)
 
-__global__ void __launch_bounds__(1024) nms_group_kernel(const float* __restrict__ dets, const float* __restrict__ scores,
-                                                         int N, int gs, float thr, unsigned char* __restrict__ kept) {
-  __shared__ BoxPre pre[kGroupMax];
-  __shared__ float sc[kGroupMax];
-  __shared__ int ord[kGroupMax];
-  __shared__ unsigned long long bits[kGroupMax][2];
-  const int g0 = blockIdx.x * gs, n = min(gs, N - g0), tid = threadIdx.x;
+// local order of group g (score descending, ties -> lower index) + per-box invariants at the sorted position
+__device__ __forceinline__ void group_rank(const float* __restrict__ dets, const float* __restrict__ scores, int g0, int n,
+                                           float* sc, int* ord, BoxPre* pre) {
+  const int tid = threadIdx.x;
   if (tid < n) sc[tid] = rank_key(__ldg(&scores[g0 + tid]));
-  if (tid < kGroupMax) bits[tid][0] = bits[tid][1] = 0ull;
   __syncthreads();
   if (tid < n) {
     const float si = sc[tid];
     int cnt = 0;
     for (int j = 0; j < n; j++) cnt += (sc[j] > si) || (sc[j] == si && j < tid);
     ord[cnt] = tid;
-    pre[cnt] = make_pre(dets + (size_t)(g0 + tid) * 5);
+    if (pre) pre[cnt] = make_pre(dets + (size_t)(g0 + tid) * 5);
   }
   __syncthreads();
-  for (int p = tid; p < n * n; p += blockDim.x) {
-    const int r = p / n, c = p - r * n;
+}
+
+// pair tests of the rows one slice owns -> bits[g][r][2] (global, every row written by exactly one CTA)
+__global__ void __launch_bounds__(1024) nms_group_pairs_kernel(const float* __restrict__ dets,
+                                                               const float* __restrict__ scores, int N, int gs, float thr,
+                                                               unsigned long long* __restrict__ gbits) {
+  __shared__ BoxPre pre[kGroupMax];
+  __shared__ float sc[kGroupMax];
+  __shared__ int ord[kGroupMax];
+  __shared__ unsigned long long bits[kGroupMax][2];
+  const int g = blockIdx.y, slice = blockIdx.x, g0 = g * gs, n = min(gs, N - g0), tid = threadIdx.x;
+  if (tid < kGroupMax) bits[tid][0] = bits[tid][1] = 0ull;
+  group_rank(dets, scores, g0, n, sc, ord, pre);
+  const int my_rows = (n - slice + kGroupSlices - 1) / kGroupSlices;  // rows slice, slice + S, ...
+  for (int p = tid; p < my_rows * n; p += blockDim.x) {
+    const int r = slice + (p / n) * kGroupSlices, c = p % n;
     if (c > r && iou_pair(pre[r], pre[c]) > thr) atomicOr(&bits[r][c >> 6], 1ull << (c & 63));  // nms_rotated_cuda.cu:62-63
+  }
+  __syncthreads();
+  for (int e = tid; e < my_rows * 2; e += blockDim.x) {
+    const int r = slice + (e >> 1) * kGroupSlices;
+    gbits[((size_t)g0 + r) * 2 + (e & 1)] = bits[r][e & 1];
+  }
+}
+
+// greedy chain of one group over its bit matrix
+__global__ void __launch_bounds__(kGroupMax) nms_group_chain_kernel(const float* __restrict__ scores, int N, int gs,
+                                                                    const unsigned long long* __restrict__ gbits,
+                                                                    unsigned char* __restrict__ kept) {
+  __shared__ float sc[kGroupMax];
+  __shared__ int ord[kGroupMax];
+  __shared__ unsigned long long bits[kGroupMax][2];
+  const int g = blockIdx.x, g0 = g * gs, n = min(gs, N - g0), tid = threadIdx.x;
+  group_rank(nullptr, scores, g0, n, sc, ord, nullptr);
+  if (tid < n) {
+    bits[tid][0] = gbits[((size_t)g0 + tid) * 2];
+    bits[tid][1] = gbits[((size_t)g0 + tid) * 2 + 1];
   }
   __syncthreads();
   if (tid == 0) {
@@ -475,7 +506,9 @@ inline NmsLayout nms_layout(int N) {
   l.order_off = 0;
   l.pre_off = align_up(l.order_off + sizeof(int) * (size_t)N, 256);
   l.mask_off = align_up(l.pre_off + sizeof(BoxPre) * (size_t)N, 256);
-  l.total = align_up(l.mask_off + sizeof(unsigned long long) * (size_t)N * cb, 256);
+  // N x cb mask words; the grouped variant needs 2 words per box + N flags instead
+  const size_t mask_bytes = sizeof(unsigned long long) * (size_t)N * cb, grouped_bytes = (size_t)17 * N + 256;
+  l.total = align_up(l.mask_off + (mask_bytes > grouped_bytes ? mask_bytes : grouped_bytes), 256);
   return l;
 }
 
@@ -515,9 +548,14 @@ extern "C" int v3d_nms_rotated_grouped(const float* dets, const float* scores, i
   char* ws = static_cast<char*>(workspace);
   int* order = reinterpret_cast<int*>(ws + l.order_off);
   BoxPre* pre = reinterpret_cast<BoxPre*>(ws + l.pre_off);
-  unsigned char* kept = reinterpret_cast<unsigned char*>(ws + l.mask_off);  // N bytes of the mask area
+  // the mask area holds the per-group bit matrices (2 words per box) followed by the N kept flags
+  const int n_groups = ceil_div(N, group_size);
+  unsigned long long* gbits = reinterpret_cast<unsigned long long*>(ws + l.mask_off);
+  unsigned char* kept = reinterpret_cast<unsigned char*>(ws + l.mask_off + sizeof(unsigned long long) * 2 * (size_t)N);
   nms_rank_kernel<<<ceil_div(N, 8), 256, 0, st>>>(dets, scores, N, order, pre);
-  nms_group_kernel<<<ceil_div(N, group_size), 1024, 0, st>>>(dets, scores, N, group_size, iou_threshold, kept);
+  nms_group_pairs_kernel<<<dim3(kGroupSlices, n_groups), 1024, 0, st>>>(dets, scores, N, group_size, iou_threshold,
+                                                                        gbits);
+  nms_group_chain_kernel<<<n_groups, kGroupMax, 0, st>>>(scores, N, group_size, gbits, kept);
   nms_compact_kernel<<<1, 1024, 0, st>>>(order, kept, N, reinterpret_cast<long long*>(keep), num_keep);
   return check_launch();
 }
