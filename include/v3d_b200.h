@@ -267,8 +267,10 @@ V3D_API int v3d_second_head_decode(const float* reg_map, const long long* reg_st
  *   v3d_second_head_decode_compact : decode + BEV + NMS group offsets from the compact deltas */
 V3D_API int v3d_head_cls_logits(const float* fmap_nhwc, int B, int hw, int C, const float* weight,
                                 const float* bias, int n_out, float* logits, v3d_stream_t stream);
+V3D_API size_t v3d_topk_rows_workspace_bytes(int rows, int k);
 V3D_API int v3d_topk_rows(const float* values, int rows, int row_len, int k, float* out_values,
-                          int64_t* out_index, v3d_stream_t stream);
+                          int64_t* out_index, void* workspace /* may be NULL: single-pass */,
+                          size_t workspace_bytes, v3d_stream_t stream);
 V3D_API int v3d_head_reg_gather(const float* fmap_nhwc, int C, const float* w_reg, const float* b_reg,
                                 const float* top_logits, const int64_t* anchor_idx, int B, int n_cls, int n_yaw,
                                 int ny, int nx, int topk, float* deltas, float* scores, v3d_stream_t stream);

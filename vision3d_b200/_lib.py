@@ -48,7 +48,8 @@ SIGNATURES = {
     "v3d_sparse_to_dense_nhwc": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P, c_size_t, P]),
     "v3d_second_head_decode": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P]),
     "v3d_head_cls_logits": (c_int, [P, c_int, c_int, c_int, P, P, c_int, P, P]),
-    "v3d_topk_rows": (c_int, [P, c_int, c_int, c_int, P, P, P]),
+    "v3d_topk_rows_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "v3d_topk_rows": (c_int, [P, c_int, c_int, c_int, P, P, P, c_size_t, P]),
     "v3d_head_reg_gather": (c_int, [P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P]),
     "v3d_second_head_decode_compact": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P]),
     "v3d_pack_detections": (c_int, [P, P, P, P, P, c_int, c_int, c_int, P, c_int, P, P]),

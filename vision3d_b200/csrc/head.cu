@@ -185,8 +185,12 @@ __device__ __forceinline__ unsigned int order_key(float v) {
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
+// `segs` > 1: the launch treats every row as `segs` consecutive segments of L elements (one CTA each) and
+// reports indices relative to the whole row; `idx_map` != null: the reported index is idx_map[row * L + i]
+// (second stage over the first stage's candidates).
 __global__ void __launch_bounds__(1024) topk_rows_kernel(const float* __restrict__ values, int L, int k,
-                                                         float* __restrict__ out_v, long long* __restrict__ out_i) {
+                                                         float* __restrict__ out_v, long long* __restrict__ out_i, int segs,
+                                                         const long long* __restrict__ idx_map) {
   __shared__ unsigned int hist[256];
   __shared__ unsigned int s_sel[3];   // [0] selected digit, [1] remaining, [2] 1 = the selection is already exact
   __shared__ unsigned long long s_pairs[kTopkMax];
@@ -309,7 +313,8 @@ __global__ void __launch_bounds__(1024) topk_rows_kernel(const float* __restrict
   if (tid < k) {
     const unsigned long long comp = s_pairs[tid];
     const unsigned int idx = ~(unsigned int)(comp & 0xffffffffull);
-    out_i[(size_t)blockIdx.x * k + tid] = (long long)idx;
+    out_i[(size_t)blockIdx.x * k + tid] = idx_map ? idx_map[(size_t)blockIdx.x * L + idx]
+                                                  : (long long)idx + (long long)(blockIdx.x % segs) * L;
     out_v[(size_t)blockIdx.x * k + tid] = __ldg(row + idx);
   }
 }
@@ -395,12 +400,32 @@ extern "C" int v3d_head_cls_logits(const float* fmap_nhwc, int B, int hw, int C,
   return V3D_ERR_INVALID_ARGUMENT;
 }
 
+constexpr int kTopkSegs = 8;
+
+extern "C" size_t v3d_topk_rows_workspace_bytes(int rows, int k) {
+  if (rows <= 0 || k <= 0) return 0;
+  return (size_t)rows * kTopkSegs * k * (sizeof(float) + sizeof(long long)) + 256;
+}
+
 extern "C" int v3d_topk_rows(const float* values, int rows, int row_len, int k, float* out_values, int64_t* out_index,
-                             v3d_stream_t stream) {
+                             void* workspace, size_t workspace_bytes, v3d_stream_t stream) {
   if (!values || !out_values || !out_index || rows <= 0 || row_len <= 0) return V3D_ERR_INVALID_ARGUMENT;
   if (k <= 0 || k > kTopkMax || k > row_len) return V3D_ERR_INVALID_ARGUMENT;
-  topk_rows_kernel<<<rows, 1024, 0, as_stream(stream)>>>(values, row_len, k, out_values,
-                                                        reinterpret_cast<long long*>(out_index));
+  cudaStream_t st = as_stream(stream);
+  long long* out_i = reinterpret_cast<long long*>(out_index);
+  const int seg_len = row_len / kTopkSegs;
+  // long rows: 8 CTAs per row select k candidates each, a second launch picks k of the 8 k (a single CTA per row
+  // streams the whole row several times: 70 us for 16 rows of 70 400). Ties still go to the lower index: the
+  // candidate array is ordered by (segment, rank inside the segment).
+  if (workspace && row_len % kTopkSegs == 0 && seg_len >= 4 * k && kTopkSegs * k >= k &&
+      workspace_bytes >= v3d_topk_rows_workspace_bytes(rows, k)) {
+    long long* cand_i = static_cast<long long*>(workspace);
+    float* cand_v = reinterpret_cast<float*>(cand_i + (size_t)rows * kTopkSegs * k);
+    topk_rows_kernel<<<rows * kTopkSegs, 1024, 0, st>>>(values, seg_len, k, cand_v, cand_i, kTopkSegs, nullptr);
+    topk_rows_kernel<<<rows, 1024, 0, st>>>(cand_v, kTopkSegs * k, k, out_values, out_i, 1, cand_i);
+    return check_launch();
+  }
+  topk_rows_kernel<<<rows, 1024, 0, st>>>(values, row_len, k, out_values, out_i, 1, nullptr);
   return check_launch();
 }
 

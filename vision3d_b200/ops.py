@@ -506,16 +506,21 @@ def head_cls_logits(fmap, weight, bias, out=None):
     return out
 
 
-def topk_rows(values, k, out_values=None, out_index=None):
-    """values (rows, L) f32 -> (top values (rows,k) descending, indices (rows,k) int64); ties -> lower index."""
+def topk_rows(values, k, out_values=None, out_index=None, workspace=None):
+    """values (rows, L) f32 -> (top values (rows,k) descending, indices (rows,k) int64); ties -> lower index.
+    `workspace` (uint8, v3d_topk_rows_workspace_bytes) enables the two-stage path for long rows."""
     rows, L = values.shape
     if out_values is None:
         out_values = torch.empty((rows, k), dtype=_F32, device=values.device)
     if out_index is None:
         out_index = torch.empty((rows, k), dtype=torch.int64, device=values.device)
+    if workspace is None:
+        workspace = torch.empty(_lib.load().v3d_topk_rows_workspace_bytes(rows, int(k)), dtype=torch.uint8,
+                                device=values.device)
     with torch.cuda.device(values.device):
         check(_lib.load().v3d_topk_rows(values.data_ptr(), rows, L, int(k), out_values.data_ptr(),
-                                        out_index.data_ptr(), _stream()), "v3d_topk_rows")
+                                        out_index.data_ptr(), workspace.data_ptr(), workspace.numel(), _stream()),
+              "v3d_topk_rows")
     return out_values, out_index
 
 

@@ -400,6 +400,8 @@ class SecondEngine:
         self._logits = torch.empty((B, n_out, ny * nx), dtype=torch.float32, device=dev)
         self._top_logits = torch.empty((B * n_cls, cfg.TOPK), dtype=torch.float32, device=dev)
         self._a_idx = torch.zeros((B * n_cls, cfg.TOPK), dtype=torch.int64, device=dev)
+        self._topk_ws = torch.empty(ops._lib.load().v3d_topk_rows_workspace_bytes(B * n_cls, cfg.TOPK),
+                                    dtype=torch.uint8, device=dev)
         self._deltas = torch.empty((self.N, 7), dtype=torch.float32, device=dev)
         self._scores_buf = torch.empty(self.N, dtype=torch.float32, device=dev)
         # ---- RPN (stays cuDNN): "module" = the nn.Sequential as is; "fused" = eval BatchNorm2d folded into
@@ -510,8 +512,8 @@ class SecondEngine:
         plan.append(("rpn(cudnn)", 0, self._rpn))
         native_head = self.fused_head and self.rpn_mode == "fused_nhwc"  # logits, top-k, reg gather, decode
         plan.append(("heads+topk+decode" if native_head else "heads+topk(torch)+decode",
-                     4 if native_head else (1 if self.fused_head else 0), self._head))
-        plan.append(("nms_rotated", 3, self._nms))
+                     5 if native_head else (1 if self.fused_head else 0), self._head))
+        plan.append(("nms_rotated", 4 if (self.grouped_nms and cfg.TOPK <= 128) else 3, self._nms))
         plan.append(("pack_result", 1 if self.fused_head else 0, self._pack))
         self.plan = plan
         self.kernel_launches = sum(p[1] for p in plan)
@@ -545,7 +547,7 @@ class SecondEngine:
             # (sigmoid is monotonic), regression head evaluated only at the top-k anchors, decode
             ny, nx = fmap.shape[2], fmap.shape[3]
             ops.head_cls_logits(fmap, self._w_cls, self._b_cls, out=self._logits)
-            ops.topk_rows(self._logits.view(B * n_cls, -1), cfg.TOPK, self._top_logits, self._a_idx)
+            ops.topk_rows(self._logits.view(B * n_cls, -1), cfg.TOPK, self._top_logits, self._a_idx, self._topk_ws)
             ops.head_reg_gather(fmap, self._w_reg, self._b_reg, self._top_logits, self._a_idx, n_cls, cfg.NUM_YAW,
                                 cfg.TOPK, self._deltas, self._scores_buf)
             ops.second_head_decode_compact(self._deltas, self.anchors, self._a_idx, B, n_cls, cfg.NUM_YAW, ny, nx,
