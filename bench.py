@@ -122,17 +122,25 @@ def cpu_frames_per_s(frames, warm=1):
     cfg, model = build_cpu_model()
     anchors = second.make_anchors(cfg)
     # give the CPU arm its best thread count (many-core boxes lose to oversubscription on these small GEMMs)
-    cores = os.cpu_count() or 1
+    # (thread counts are tried in ASCENDING order and the search stops as soon as more threads stop helping: a
+    # container whose cpu_count is far above its CPU quota would otherwise spend minutes in one oversubscribed trial)
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
     best = (None, float("inf"))
     warm_cloud = [synth.make_cloud(900, PTS_PER_FRAME)]
+    torch.set_num_threads(min(cores, 8))
     second_cpu.infer(model, warm_cloud, anchors)
-    for nt in sorted({cores, min(cores, 32), min(cores, 16), min(cores, 8)}, reverse=True):
+    for nt in sorted({min(cores, 4), min(cores, 8), min(cores, 16), min(cores, 32), min(cores, 64), cores}):
         torch.set_num_threads(nt)
         t = time.perf_counter()
         second_cpu.infer(model, warm_cloud, anchors)
         dt = time.perf_counter() - t
         if dt < best[1]:
             best = (nt, dt)
+        elif dt > 1.15 * best[1]:
+            break
     torch.set_num_threads(best[0])
     for i in range(max(0, warm - 1)):
         second_cpu.infer(model, [synth.make_cloud(901 + i, PTS_PER_FRAME)], anchors)
