@@ -252,3 +252,21 @@ def test_bf16x3_split_error_model():
         assert errs["rn"] < 1e-5, errs
         assert errs["rn"] * 14 ** 0.5 < 1e-4          # 14 layers in quadrature stay inside the contract
         assert errs["trunc"] > 3 * errs["rn"]
+
+
+def test_anchor_grid_and_box_decode_match_reference_golden():
+    """vision3d_b200.second.make_anchors / decode_boxes vs vectors produced by the reference's own
+    core/anchor_generator.py and core/box_encode.py (tests/golden/make_head_golden.py), bit for bit."""
+    import os
+    import torch
+    from vision3d_b200 import second
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "head_golden.npz"))
+    for tag, cfg in (("car", second.car_config()), ("three", second.three_class_config())):
+        anchors = second.make_anchors(cfg)
+        assert list(anchors.shape) == gold[tag + "_shape"].tolist()
+        flat = anchors.reshape(-1, 7)
+        assert np.array_equal(flat.double().sum(0).numpy(), gold[tag + "_colsum"])
+        idx = torch.from_numpy(gold[tag + "_idx"])
+        assert np.array_equal(flat[idx].numpy(), gold[tag + "_anchors"])
+        dec = second.decode_boxes(torch.from_numpy(gold[tag + "_deltas"]), flat[idx])
+        assert np.array_equal(dec.numpy(), gold[tag + "_decoded"])
