@@ -270,3 +270,17 @@ def test_anchor_grid_and_box_decode_match_reference_golden():
         assert np.array_equal(flat[idx].numpy(), gold[tag + "_anchors"])
         dec = second.decode_boxes(torch.from_numpy(gold[tag + "_deltas"]), flat[idx])
         assert np.array_equal(dec.numpy(), gold[tag + "_decoded"])
+
+
+def test_batched_nms_wrapper_matches_reference_golden():
+    """The group-offset trick (synth.apply_group_offsets, fp32) + oracle NMS (host variant) vs the keep lists the
+    reference's own batched_nms_rotated wrapper produced on its own compiled CPU ops
+    (tests/golden/make_batched_nms_golden.py)."""
+    import os
+    from vision3d_b200 import synth
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "batched_nms_golden.npz"))
+    for case in range(3):
+        boxes, scores, idxs = (gold["c%d_%s" % (case, k)] for k in ("boxes", "scores", "idxs"))
+        off = synth.apply_group_offsets(boxes, idxs)
+        keep = oracle.nms_rotated(off, scores, 0.01, 0)
+        assert np.array_equal(keep, gold["c%d_keep" % case]), case
