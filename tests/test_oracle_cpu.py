@@ -284,3 +284,46 @@ def test_batched_nms_wrapper_matches_reference_golden():
         off = synth.apply_group_offsets(boxes, idxs)
         keep = oracle.nms_rotated(off, scores, 0.01, 0)
         assert np.array_equal(keep, gold["c%d_keep" % case]), case
+
+
+def test_proposal_stage_matches_reference_proposal_layer_golden():
+    """HeadB200 (1x1 heads, reshape order, sigmoid, top-k, gather, decode) + the group-offset trick + oracle NMS +
+    per-class thresholds, against what the reference's own ProposalLayer.inference returned for the same weights
+    and the same deterministic feature map (tests/golden/make_proposal_golden.py)."""
+    import os
+    import sys
+    import torch
+    from vision3d_b200 import second
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    from make_proposal_golden import feature_map
+    gold = np.load(os.path.join(here, "golden", "proposal_golden.npz"))
+    for tag, cfg in (("three", second.three_class_config()), ("car", second.car_config())):
+        head = second.HeadB200(cfg).eval()
+        head.load_state_dict({k[len(tag) + 3:]: torch.from_numpy(gold[k]) for k in gold.files
+                              if k.startswith(tag + "_w_")})
+        anchors = second.make_anchors(cfg)
+        fmap = torch.from_numpy(feature_map(2, cfg.PROPOSAL_C_IN, anchors.shape[2], anchors.shape[3]))
+        with torch.no_grad():
+            boxes, scores = head.candidates(fmap, anchors)           # (B, n_cls, K, 7), (B, n_cls, K)
+        B, n_cls, K = scores.shape
+        boxes, scores = boxes.reshape(-1, 7), scores.reshape(-1)
+        b_idx = torch.arange(B)[:, None, None].expand(-1, n_cls, K).reshape(-1)
+        c_idx = torch.arange(n_cls)[None, :, None].expand(B, -1, K).reshape(-1)
+        nms_in = second.group_offsets(boxes[:, [0, 1, 3, 4, 6]], c_idx + n_cls * b_idx)
+        keep = torch.from_numpy(oracle.nms_rotated(nms_in.numpy(), scores.numpy(), cfg.NMS_THRESH, 0).astype(np.int64))
+        thr = torch.tensor([a["score_thresh"] for a in cfg.ANCHORS])
+        m = scores[keep] > thr[c_idx[keep]]
+        k = keep[m]
+        assert np.array_equal(scores[k].numpy(), gold[tag + "_scores"])   # same order of (distinct) scores
+
+        def canon(bx, sc, bi, ci):
+            # boxes with EQUAL scores come out of torch's unstable descending sort in an unspecified order
+            # (nms_rotated_cpu.cpp:30): compare rows after ordering ties by (frame, class, box)
+            rows = np.concatenate([sc[:, None], bi[:, None], ci[:, None], bx], 1).astype(np.float64)
+            order = np.lexsort([rows[:, c] for c in range(rows.shape[1] - 1, 0, -1)] + [-rows[:, 0]])
+            return rows[order]
+
+        mine = canon(boxes[k].numpy(), scores[k].numpy(), b_idx[k].numpy(), c_idx[k].numpy())
+        ref = canon(gold[tag + "_boxes"], gold[tag + "_scores"], gold[tag + "_batch_idx"], gold[tag + "_class_idx"])
+        assert np.array_equal(mine, ref)
