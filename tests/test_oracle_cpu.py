@@ -327,3 +327,11 @@ def test_proposal_stage_matches_reference_proposal_layer_golden():
         mine = canon(boxes[k].numpy(), scores[k].numpy(), b_idx[k].numpy(), c_idx[k].numpy())
         ref = canon(gold[tag + "_boxes"], gold[tag + "_scores"], gold[tag + "_batch_idx"], gold[tag + "_class_idx"])
         assert np.array_equal(mine, ref)
+
+
+def test_vfe_mean_matches_reference_golden():
+    """oracle.vfe_mean (what the fused voxelize epilogue is checked against) vs the reference's own
+    VoxelFeatureExtractor.forward (tests/golden/make_vfe_golden.py), bit for bit."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vfe_golden.npz"))
+    assert np.array_equal(oracle.vfe_mean(gold["voxels"], gold["occupancy"]), gold["mean"])
