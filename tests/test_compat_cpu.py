@@ -58,3 +58,29 @@ def test_mirror_matches_reference_anchors_and_parameter_names():
     for key in ["cnn.blocks.0.0.0.weight", "cnn.blocks.3.3.0.weight", "cnn.blocks.2.1.1.running_mean",
                 "rpn.down_block.1.weight", "rpn.up_block.0.weight", "head.conv_cls.bias", "head.conv_reg.weight"]:
         assert key in names, key
+
+
+def test_rpn_mirror_equals_reference_rpn_forward():
+    """RPNB200 (the module the engine folds into cudnn conv+bias+ReLU calls) vs the reference's own RPN
+    (detector/second.py:47-93) with the same state_dict, eval mode, on the CPU: identical outputs."""
+    import torch
+    import vision3d_b200.compat as compat
+    compat.install()
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from vision3d.detector.second import RPN
+    from vision3d_b200 import second
+    torch.manual_seed(11)
+    ref = RPN().eval()
+    with torch.no_grad():
+        for m in ref.modules():  # non-trivial BN statistics
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.1)
+                m.running_var.uniform_(0.5, 1.5)
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.normal_(0, 0.1)
+    mine = second.RPNB200().eval()
+    mine.load_state_dict(ref.state_dict())          # same parameter names and shapes
+    x = torch.randn(1, 128, 20, 24)
+    with torch.no_grad():
+        assert torch.equal(mine(x), ref(x))
