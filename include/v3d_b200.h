@@ -244,6 +244,48 @@ V3D_API int v3d_query_and_group(const float* xyz, const float* new_xyz, const fl
                                 const int* idx, int B, int C, int N, int M, int nsample, float* out,
                                 v3d_stream_t stream);
 
+/* a7+a8 fused: PV_RCNN.sample_keypoints (detector/model.py:46-56). `points` rows are `point_stride` floats
+ * (3 = xyz, 4 = x,y,z,intensity as core/preprocess.py emits them; stride 4 is read with 128-bit loads, base 16-byte
+ * aligned). Writes idx[B,m] and, when keypoints != NULL, keypoints[B,m,3] = points[idx, :3] (gather_operation +
+ * the two transposes of model.py:54-55). */
+V3D_API int v3d_fps_keypoints(const float* points, int point_stride, int B, int N, int m, int* idx,
+                              float* keypoints, v3d_stream_t stream);
+
+/* a9 for a whole PointnetSAModuleMSG (detector/model.py:39-43,64; detector/roi_grid_pool.py:28-32,68): all
+ * `n_radii` (<= 4) ball queries of the module in one pass over the sources, one warp per query, same results as
+ * n_radii calls of v3d_ball_query. Sources: row_offsets == NULL -> dense (B, N, point_stride) batch; else frame b
+ * owns rows [row_offsets[b], row_offsets[b+1]) of a packed (rows, point_stride) array (DEVICE int[B+1]) and the
+ * indices written are relative to the frame's first row -- this replaces pad_batch (detector/sparse_cnn.py:118-126).
+ * radii_host / nsamples_host / idx_host are HOST arrays of n_radii entries (idx_host[r] = DEVICE int[B,M,ns_r]). */
+V3D_API int v3d_ball_query_msg(const float* xyz, int point_stride, const int* row_offsets, const float* new_xyz,
+                               int B, int N, int M, int n_radii, const float* radii_host,
+                               const int* nsamples_host, int* const* idx_host, v3d_stream_t stream);
+
+/* a10 QueryAndGroup(use_xyz=True) reading ROW-major sources: xyz (rows, xyz_stride), feat rows of C floats
+ * `feat_stride` floats apart (C may be 0; feat may alias xyz, e.g. the intensity column of (x,y,z,i) points),
+ * dense (row = b*N + idx) or ragged (row = row_offsets[b] + idx) -> out[B, 3+C, M, nsample]. Spares the
+ * `features.transpose(1, 2).contiguous()` of detector/model.py:62 for the row-major sparse levels. */
+V3D_API int v3d_query_and_group_rows(const float* xyz, int xyz_stride, const float* feat, int feat_stride, int C, int N,
+                                     const int* row_offsets, const float* new_xyz, const int* idx, int B, int M,
+                                     int nsample, float* out, v3d_stream_t stream);
+
+/* a15 on the device: offsets[b] = first row of frame b in a (b,z,y,x)-ordered index list, offsets[B] = n_rows
+ * (= torchsearchsorted.searchsorted(batch_index, arange(B+1)), compute_pad_amounts, detector/sparse_cnn.py:107-116,
+ * without its .cpu().numpy() round trip). */
+V3D_API int v3d_batch_offsets(const int* indices, const int* n_rows, int capacity_rows, int B, int* offsets,
+                              v3d_stream_t stream);
+
+/* to_global (detector/sparse_cnn.py:91-105): xyz[i] = float(x,y,z of indices[i]) * voxel_size_host + offset_host
+ * (voxel_size_host = base voxel size * level stride, fp32, xyz order). */
+V3D_API int v3d_to_global(const int* indices, const int* n_rows, int capacity_rows, const float* voxel_size_host,
+                          const float* offset_host, float* xyz, v3d_stream_t stream);
+
+/* pad_batch / pad_for_batch (detector/sparse_cnn.py:118-126, core/preprocess.py:35-45): ragged rows (rows, C) ->
+ * dense out[B, frame_capacity, C]; a frame with fewer rows is filled with uniformly drawn duplicates of its own
+ * rows (counter-based RNG keyed by (seed, frame, slot): tensors padded with the same seed stay row-paired). */
+V3D_API int v3d_pad_batch(const float* src, int C, const int* row_offsets, int B, int frame_capacity,
+                          unsigned long long seed, float* out, v3d_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Glue between the RPN heads and a12 for the SECOND inference path (engine-internal, replaces ~55 tiny
  * torch launches): ProposalLayer._decode + the BEV slice + batched_nms_rotated's coordinate offsets

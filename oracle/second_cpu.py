@@ -44,6 +44,7 @@ def sparse_middle(model, feat, coords, batch_size, return_levels=False):
     idx = np.ascontiguousarray(coords, np.int32)
     x = feat
     levels = [(idx, shape)]
+    level_feats = [feat]   # x0 .. x4 as SparseCNNBase.forward names them (sparse_cnn.py:135-146)
     for blk in model.cnn.blocks:
         nbr_subm = None
         for seq in blk:
@@ -60,10 +61,13 @@ def sparse_middle(model, feat, coords, batch_size, return_levels=False):
                 idx = out_idx
                 levels.append((idx, shape))
             x = _bn_relu(x, bn)
+        level_feats.append(x)
     dense = torch.zeros((batch_size, x.shape[1], *shape), dtype=torch.float32)
     ii = torch.from_numpy(idx.astype(np.int64))
     dense[ii[:, 0], :, ii[:, 1], ii[:, 2], ii[:, 3]] = x
     bev = dense.view(batch_size, -1, shape[1], shape[2])
+    if return_levels == "features":
+        return bev, levels, level_feats
     if return_levels:
         return bev, levels, x
     return bev

@@ -59,6 +59,12 @@ SIGNATURES = {
     "v3d_ball_query": (c_int, [P, P, c_int, c_int, c_int, c_float, c_int, P, P]),
     "v3d_group": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P, P]),
     "v3d_query_and_group": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P]),
+    "v3d_fps_keypoints": (c_int, [P, c_int, c_int, c_int, c_int, P, P, P]),
+    "v3d_ball_query_msg": (c_int, [P, c_int, P, P, c_int, c_int, c_int, c_int, P, P, P, P]),
+    "v3d_query_and_group_rows": (c_int, [P, c_int, P, c_int, c_int, c_int, P, P, P, c_int, c_int, c_int, P, P]),
+    "v3d_batch_offsets": (c_int, [P, P, c_int, c_int, P, P]),
+    "v3d_to_global": (c_int, [P, P, c_int, P, P, P, P]),
+    "v3d_pad_batch": (c_int, [P, c_int, P, c_int, c_int, ctypes.c_ulonglong, P, P]),
 }
 
 _lib = None

@@ -94,14 +94,23 @@ class _QueryGroupFused(Function):
 
     @staticmethod
     def backward(ctx, grad_out):
+        """Upstream QueryAndGroup is differentiable w.r.t. xyz and new_xyz too (grouping_operation(xyz) minus
+        new_xyz): channels 0..2 scatter-add into xyz[idx] and sum (negated) over the samples into new_xyz."""
         (idx,) = ctx.saved_tensors
-        g_feat = None
-        if ctx.has_feat:
-            B, CT, M, ns = grad_out.shape
+        B, CT, M, ns = grad_out.shape
+        flat = idx.long().view(B, 1, M * ns)
+        g_xyz = g_new = g_feat = None
+        if ctx.needs_input_grad[0]:
+            g = grad_out.new_zeros((B, 3, ctx.n))
+            g.scatter_add_(2, flat.expand(-1, 3, -1), grad_out[:, :3].reshape(B, 3, M * ns))
+            g_xyz = g.transpose(1, 2).contiguous()
+        if ctx.needs_input_grad[1]:
+            g_new = -grad_out[:, :3].sum(-1).transpose(1, 2).contiguous()
+        if ctx.has_feat and ctx.needs_input_grad[2]:
             gf = grad_out[:, 3:].reshape(B, CT - 3, M * ns)
             g_feat = grad_out.new_zeros((B, CT - 3, ctx.n))
-            g_feat.scatter_add_(2, idx.long().view(B, 1, M * ns).expand(-1, CT - 3, -1), gf)
-        return None, None, g_feat, None
+            g_feat.scatter_add_(2, flat.expand(-1, CT - 3, -1), gf)
+        return g_xyz, g_new, g_feat, None
 
 
 class QueryAndGroup(nn.Module):

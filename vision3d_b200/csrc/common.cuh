@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/v3d_b200.h"
 
 #if defined(__CUDA_ARCH__) && !defined(__CUDA_ARCH_FEAT_SM100_ALL) && (__CUDA_ARCH__ != 1000)
@@ -32,6 +34,20 @@ inline int check_launch() {
       return V3D_ERR_CUDA;                 \
     }                                      \
   } while (0)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE property and the wrappers accept tensors on
+// any device of the process: remember per (call site, device) whether it was applied. Setting the attribute is
+// idempotent, so two threads racing on the first call both set it and both mark it (no lock needed).
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> mask{0ull};
+  static unsigned long long bit() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return 1ull << (d & 63);
+  }
+  bool needed() const { return (mask.load(std::memory_order_acquire) & bit()) == 0ull; }
+  void done() { mask.fetch_or(bit(), std::memory_order_release); }
+};
 
 inline cudaStream_t as_stream(v3d_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

@@ -186,10 +186,10 @@ extern "C" int v3d_sparse_to_dense(const float* feat, const int* indices, const 
                                           shape_host[0], shape_host[1], shape_host[2], B, cellmap);
   const size_t smem = sizeof(float) * kCells * (C + 1);
   if (smem > 96 * 1024) return V3D_ERR_INVALID_ARGUMENT;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.needed()) {
     V3D_CUDA_TRY(cudaFuncSetAttribute(dense_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr_set = true;
+    attr_once.done();
   }
   dense_write_kernel<<<dim3((unsigned)ceil_div((int)vol, kCells), B), 256, smem, st>>>(feat, cellmap, C, (int)vol, out);
   return check_launch();

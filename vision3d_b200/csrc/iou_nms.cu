@@ -522,9 +522,15 @@ extern "C" int v3d_box_iou_rotated(const float* boxes1, int M, const float* boxe
   if (M < 0 || N < 0) return V3D_ERR_INVALID_ARGUMENT;
   if (M == 0 || N == 0) return V3D_OK;  // box_iou_rotated_cuda.cu:80
   if (!boxes1 || !boxes2 || !ious) return V3D_ERR_INVALID_ARGUMENT;
-  dim3 grid(ceil_div(N, kIouTC), ceil_div(M, kIouTR));
-  if (grid.y > 65535) return V3D_ERR_INVALID_ARGUMENT;  // cf. box_iou_rotated_cuda.cu:84-95
-  box_iou_kernel<<<grid, kIouThreads, 0, as_stream(stream)>>>(boxes1, M, boxes2, N, ious);
+  // any M: the reference transposes the problem when one grid dimension would overflow
+  // (box_iou_rotated_cuda.cu:84-95); here the rows are simply cut into launches of <= 65535 row tiles
+  constexpr int kRowsPerLaunch = 65535 * kIouTR;
+  for (int m0 = 0; m0 < M; m0 += kRowsPerLaunch) {
+    const int m = M - m0 < kRowsPerLaunch ? M - m0 : kRowsPerLaunch;
+    dim3 grid(ceil_div(N, kIouTC), ceil_div(m, kIouTR));
+    box_iou_kernel<<<grid, kIouThreads, 0, as_stream(stream)>>>(boxes1 + (size_t)m0 * 5, m, boxes2, N,
+                                                                ious + (size_t)m0 * N);
+  }
   return check_launch();
 }
 
@@ -584,10 +590,10 @@ extern "C" int v3d_nms_rotated(const float* dets, const float* scores, int N, fl
       pre, N, iou_threshold, cb, reinterpret_cast<unsigned int*>(mask));
   const size_t smem_fast = sizeof(unsigned long long) * (((size_t)cb + 1) / 2 * 2 + 2 * (size_t)kTile * cb);
   if (smem_fast <= 200 * 1024) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.needed()) {
       V3D_CUDA_TRY(cudaFuncSetAttribute(nms_scan_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr_set = true;
+      attr_once.done();
     }
     nms_scan_smem_kernel<<<1, kScanThreads, smem_fast, st>>>(mask, order, N, cb, reinterpret_cast<long long*>(keep),
                                                             num_keep);

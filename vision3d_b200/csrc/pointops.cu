@@ -41,12 +41,13 @@ __device__ __forceinline__ bool better(float d1, int i1, float d2, int i2) {
 
 template <int PPT>
 __global__ void __cluster_dims__(kFpsCluster, 1, 1) __launch_bounds__(kFpsThreads)
-    fps_cluster_kernel(const float* __restrict__ xyz, int N, int m, int* __restrict__ out) {
+    fps_cluster_kernel(const float* __restrict__ xyz, int stride, int N, int m, int* __restrict__ out,
+                       float* __restrict__ out_xyz) {
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int b = blockIdx.x / kFpsCluster;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float* P = xyz + (size_t)b * N * 3;
+  const float* P = xyz + (size_t)b * N * stride;
 
   __shared__ Cand cand[2][kFpsCluster];  // written by every CTA of the cluster through DSMEM
   __shared__ float wd[kFpsThreads / 32];
@@ -60,9 +61,16 @@ __global__ void __cluster_dims__(kFpsCluster, 1, 1) __launch_bounds__(kFpsThread
   for (int k = 0; k < PPT; k++) {
     const int i = s0 + tid + k * kFpsThreads;
     if (i < N) {
-      px[k] = P[3 * i];
-      py[k] = P[3 * i + 1];
-      pz[k] = P[3 * i + 2];
+      if (stride == 4) {  // (x, y, z, intensity) rows as the preprocessor emits them: one 128-bit load per point
+        const float4 q = __ldg(reinterpret_cast<const float4*>(P) + i);
+        px[k] = q.x;
+        py[k] = q.y;
+        pz[k] = q.z;
+      } else {
+        px[k] = P[(size_t)stride * i];
+        py[k] = P[(size_t)stride * i + 1];
+        pz[k] = P[(size_t)stride * i + 2];
+      }
       md[k] = 1e10f;
     } else {
       px[k] = py[k] = pz[k] = 0.f;
@@ -70,7 +78,14 @@ __global__ void __cluster_dims__(kFpsCluster, 1, 1) __launch_bounds__(kFpsThread
     }
   }
   float cx = P[0], cy = P[1], cz = P[2];
-  if (rank == 0 && tid == 0) out[(size_t)b * m] = 0;
+  if (rank == 0 && tid == 0) {
+    out[(size_t)b * m] = 0;
+    if (out_xyz) {  // gather_operation fused (detector/model.py:54): the winner's coordinates are at hand
+      out_xyz[(size_t)b * m * 3] = cx;
+      out_xyz[(size_t)b * m * 3 + 1] = cy;
+      out_xyz[(size_t)b * m * 3 + 2] = cz;
+    }
+  }
   cluster.sync();
 
   for (int j = 1; j < m; j++) {
@@ -169,7 +184,15 @@ __global__ void __cluster_dims__(kFpsCluster, 1, 1) __launch_bounds__(kFpsThread
     cx = cand[par][gr].x;
     cy = cand[par][gr].y;
     cz = cand[par][gr].z;
-    if (rank == 0 && tid == 0) out[(size_t)b * m + j] = gi;
+    if (rank == 0 && tid == 0) {
+      out[(size_t)b * m + j] = gi;
+      if (out_xyz) {
+        float* o = out_xyz + ((size_t)b * m + j) * 3;
+        o[0] = cx;
+        o[1] = cy;
+        o[2] = cz;
+      }
+    }
   }
 }
 
@@ -260,9 +283,176 @@ __global__ void __launch_bounds__(256) query_group_kernel(const float* __restric
   out[((size_t)b * CT + c) * MS + e] = v;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// a9, multi-scale: one WARP per query, all radii of a PointnetSAModuleMSG in one pass over the sources.
+// The thread-per-query kernel above keeps 64 CTAs busy at B=8, M=2048 (5 % of the machine's thread slots) and
+// walks the sources once per radius; here 8 queries share a CTA, the lanes test 32 consecutive sources per step
+// (ballot -> hits appended in ascending index order, exactly the sequential rule), and the scan stops as soon as
+// every radius has its nsample hits. Sources may be RAGGED: frame b owns rows [row_offsets[b], row_offsets[b+1])
+// of a packed (rows, stride) array -- the layout the sparse levels already have -- so the reference's
+// pad_batch (random duplicate rows appended to make the batch dense, sparse_cnn.py:118-126) is not needed:
+// duplicates appended AFTER the real rows can only occupy slots the first hit would have filled, and they carry
+// the features of real hits of the same ball, so the max-pooled result is unchanged.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kBqWarps = 8, kBqTileW = 2048, kBqMaxR = 4;
+struct BqArgs {
+  float r2[kBqMaxR];
+  int ns[kBqMaxR];
+  int* out[kBqMaxR];
+};
+
+template <int R>
+__global__ void __launch_bounds__(kBqWarps * 32) ball_query_warp_kernel(const float* __restrict__ xyz, int stride, int N,
+                                                                        const int* __restrict__ row_offsets,
+                                                                        const float* __restrict__ new_xyz, int M, BqArgs A) {
+  __shared__ float sx[kBqTileW], sy[kBqTileW], sz[kBqTileW];
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * kBqWarps + warp;
+  int base = b * N, n = N;
+  if (row_offsets) {
+    base = __ldg(&row_offsets[b]);
+    n = __ldg(&row_offsets[b + 1]) - base;
+  }
+  const float* P = xyz + (size_t)base * stride;
+  const bool live = q < M;
+  float qx = 0.f, qy = 0.f, qz = 0.f;
+  if (live) {
+    const float* c = new_xyz + ((size_t)b * M + q) * 3;
+    qx = __ldg(c);
+    qy = __ldg(c + 1);
+    qz = __ldg(c + 2);
+  }
+  int cnt[R], first[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) cnt[r] = 0, first[r] = 0;
+  bool done = !live;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int t0 = 0; t0 < n; t0 += kBqTileW) {
+    const int nt = min(kBqTileW, n - t0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < nt; e += kBqWarps * 32) {
+      const float* s = P + (size_t)(t0 + e) * stride;
+      sx[e] = __ldg(s);
+      sy[e] = __ldg(s + 1);
+      sz[e] = __ldg(s + 2);
+    }
+    if (__syncthreads_and(done)) break;
+    if (done) continue;
+    for (int e0 = 0; e0 < nt; e0 += 32) {
+      const int e = e0 + lane;
+      const float d2 = e < nt ? dist2(qx, qy, qz, sx[e], sy[e], sz[e]) : 3.0e38f;
+      bool all_full = true;
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        if (cnt[r] >= A.ns[r]) continue;
+        const bool hit = d2 < A.r2[r];
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (m) {
+          if (cnt[r] == 0) first[r] = t0 + e0 + __ffs(m) - 1;
+          const int pos = cnt[r] + __popc(m & lt);
+          if (hit && pos < A.ns[r]) A.out[r][((size_t)b * M + q) * A.ns[r] + pos] = t0 + e;
+          cnt[r] += __popc(m);
+        }
+        all_full = all_full && cnt[r] >= A.ns[r];
+      }
+      if (all_full) {
+        done = true;
+        break;
+      }
+    }
+  }
+  if (live) {
+#pragma unroll
+    for (int r = 0; r < R; r++)  // unused slots = first hit; no hit at all = zeros (upstream zero-initialises idx)
+      for (int l = min(cnt[r], A.ns[r]) + lane; l < A.ns[r]; l += 32) A.out[r][((size_t)b * M + q) * A.ns[r] + l] = first[r];
+  }
+}
+
+// QueryAndGroup on ROW-major sources (what the sparse levels are): out[b, c, q, l] for c < 3 is
+// xyz[row][c] - new_xyz[b, q, c] and feat[row][c - 3] after, row = row_offsets[b] + idx[b, q, l] (or b*N + idx).
+// One thread per (b, q, l) walks the channels: the source row is read once, contiguously.
+__global__ void __launch_bounds__(256) query_group_rows_kernel(const float* __restrict__ xyz, int xyz_stride,
+                                                               const float* __restrict__ feat, int feat_stride, int C, int N,
+                                                               const int* __restrict__ row_offsets,
+                                                               const float* __restrict__ new_xyz,
+                                                               const int* __restrict__ idx, int M, int ns,
+                                                               float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int MS = M * ns;
+  if (e >= MS) return;
+  const int base = row_offsets ? __ldg(&row_offsets[b]) : b * N;
+  const size_t row = (size_t)base + idx[(size_t)b * MS + e];
+  const int q = e / ns;
+  const int CT = 3 + C;
+  float* o = out + (size_t)b * CT * MS + e;
+#pragma unroll
+  for (int c = 0; c < 3; c++)
+    o[(size_t)c * MS] = __fsub_rn(__ldg(&xyz[row * xyz_stride + c]), __ldg(&new_xyz[((size_t)b * M + q) * 3 + c]));
+  const float* f = feat + row * feat_stride;
+  for (int c = 0; c < C; c++) o[(size_t)(3 + c) * MS] = __ldg(&f[c]);
+}
+
+// a15 on the device: start row of every frame in a (b,z,y,x)-sorted index list = searchsorted(batch column, 0..B)
+// (compute_pad_amounts, detector/sparse_cnn.py:107-116, without its .cpu().numpy() round trip)
+__global__ void batch_offsets_kernel(const int4* __restrict__ idx, const int* __restrict__ n_rows, int cap, int B,
+                                     int* __restrict__ offsets) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > B) return;
+  const int n = min(*n_rows, cap);
+  int lo = 0, hi = n;  // first row whose batch index is >= b
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (idx[mid].x < b) lo = mid + 1; else hi = mid;
+  }
+  offsets[b] = lo;
+}
+
+// to_global (detector/sparse_cnn.py:91-105): voxel index (b,z,y,x) -> metric xyz = float(x,y,z) * voxel_size + offset,
+// evaluated as torch does (one rounded multiply, one rounded add)
+__global__ void __launch_bounds__(256) to_global_kernel(const int4* __restrict__ idx, const int* __restrict__ n_rows, int cap,
+                                                        float3 vs, float3 off, float* __restrict__ xyz) {
+  const int n = min(*n_rows, cap);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int4 c = idx[i];
+    xyz[(size_t)i * 3] = __fadd_rn(__fmul_rn((float)c.w, vs.x), off.x);
+    xyz[(size_t)i * 3 + 1] = __fadd_rn(__fmul_rn((float)c.z, vs.y), off.y);
+    xyz[(size_t)i * 3 + 2] = __fadd_rn(__fmul_rn((float)c.y, vs.z), off.z);
+  }
+}
+
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+// pad_batch / pad_for_batch (sparse_cnn.py:118-126, core/preprocess.py:35-45): ragged rows -> dense (B, cap, C),
+// frames shorter than `cap` are filled with uniformly chosen duplicates of their own rows (counter-based RNG:
+// row j of frame b picks splitmix64(seed, b, j) % count -- the same pick for every tensor padded with the same
+// seed, so padded xyz and padded features stay paired).
+__global__ void __launch_bounds__(256) pad_batch_kernel(const float* __restrict__ src, int C,
+                                                        const int* __restrict__ row_offsets, int cap,
+                                                        unsigned long long seed, float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int start = __ldg(&row_offsets[b]), cnt = __ldg(&row_offsets[b + 1]) - start;
+  const long long total = (long long)cap * C;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(e / C), c = (int)(e % C);
+    float v = 0.f;
+    if (cnt > 0) {
+      const int r = j < cnt ? j : (int)(splitmix64(seed ^ (((unsigned long long)b << 32) | (unsigned)j)) % (unsigned long long)cnt);
+      v = __ldg(&src[(size_t)(start + r) * C + c]);
+    }
+    out[((size_t)b * cap + j) * C + c] = v;
+  }
+}
+
 template <int PPT>
-int launch_fps(const float* xyz, int B, int N, int m, int* idx, cudaStream_t st) {
-  fps_cluster_kernel<PPT><<<B * kFpsCluster, kFpsThreads, 0, st>>>(xyz, N, m, idx);
+int launch_fps(const float* xyz, int stride, int B, int N, int m, int* idx, float* out_xyz, cudaStream_t st) {
+  fps_cluster_kernel<PPT><<<B * kFpsCluster, kFpsThreads, 0, st>>>(xyz, stride, N, m, idx, out_xyz);
   return check_launch();
 }
 
@@ -277,21 +467,30 @@ extern "C" size_t v3d_fps_workspace_bytes(int B, int N) {
   return 256;  // everything lives in registers / distributed shared memory
 }
 
+static int fps_dispatch(const float* xyz, int stride, int B, int N, int m, int* idx, float* out_xyz, cudaStream_t st) {
+  if (!xyz || !idx || B <= 0 || N <= 0 || m <= 0 || (stride != 3 && stride != 4)) return V3D_ERR_INVALID_ARGUMENT;
+  if (stride == 4 && (reinterpret_cast<uintptr_t>(xyz) & 15)) return V3D_ERR_INVALID_ARGUMENT;
+  const int per_cta = ceil_div(N, kFpsCluster);
+  const int ppt = ceil_div(per_cta, kFpsThreads);
+  if (ppt <= 1) return launch_fps<1>(xyz, stride, B, N, m, idx, out_xyz, st);
+  if (ppt <= 2) return launch_fps<2>(xyz, stride, B, N, m, idx, out_xyz, st);
+  if (ppt <= 4) return launch_fps<4>(xyz, stride, B, N, m, idx, out_xyz, st);
+  if (ppt <= 8) return launch_fps<8>(xyz, stride, B, N, m, idx, out_xyz, st);
+  if (ppt <= 16) return launch_fps<16>(xyz, stride, B, N, m, idx, out_xyz, st);
+  if (ppt <= 32) return launch_fps<32>(xyz, stride, B, N, m, idx, out_xyz, st);
+  return V3D_ERR_INVALID_ARGUMENT;  // > 65536 points per cloud
+}
+
 extern "C" int v3d_fps(const float* xyz, int B, int N, int m, int* idx, void* workspace, size_t workspace_bytes,
                        v3d_stream_t stream) {
   (void)workspace;
   (void)workspace_bytes;
-  if (!xyz || !idx || B <= 0 || N <= 0 || m <= 0) return V3D_ERR_INVALID_ARGUMENT;
-  cudaStream_t st = as_stream(stream);
-  const int per_cta = ceil_div(N, kFpsCluster);
-  const int ppt = ceil_div(per_cta, kFpsThreads);
-  if (ppt <= 1) return launch_fps<1>(xyz, B, N, m, idx, st);
-  if (ppt <= 2) return launch_fps<2>(xyz, B, N, m, idx, st);
-  if (ppt <= 4) return launch_fps<4>(xyz, B, N, m, idx, st);
-  if (ppt <= 8) return launch_fps<8>(xyz, B, N, m, idx, st);
-  if (ppt <= 16) return launch_fps<16>(xyz, B, N, m, idx, st);
-  if (ppt <= 32) return launch_fps<32>(xyz, B, N, m, idx, st);
-  return V3D_ERR_INVALID_ARGUMENT;  // > 65536 points per cloud
+  return fps_dispatch(xyz, 3, B, N, m, idx, nullptr, as_stream(stream));
+}
+
+extern "C" int v3d_fps_keypoints(const float* points, int point_stride, int B, int N, int m, int* idx,
+                                 float* keypoints, v3d_stream_t stream) {
+  return fps_dispatch(points, point_stride, B, N, m, idx, keypoints, as_stream(stream));
 }
 
 extern "C" int v3d_gather(const float* feat, const int* idx, int B, int C, int N, int m, float* out,
@@ -329,5 +528,71 @@ extern "C" int v3d_query_and_group(const float* xyz, const float* new_xyz, const
   const int MS = M * nsample;
   query_group_kernel<<<dim3(ceil_div(MS, 256), CT, B), 256, 0, as_stream(stream)>>>(xyz, new_xyz, feat, idx, C, N, M,
                                                                                nsample, out);
+  return check_launch();
+}
+
+extern "C" int v3d_ball_query_msg(const float* xyz, int point_stride, const int* row_offsets, const float* new_xyz, int B,
+                                  int N, int M, int n_radii, const float* radii_host, const int* nsamples_host,
+                                  int* const* idx_host, v3d_stream_t stream) {
+  if (!xyz || !new_xyz || !radii_host || !nsamples_host || !idx_host) return V3D_ERR_INVALID_ARGUMENT;
+  if (B <= 0 || B > 65535 || M <= 0 || n_radii <= 0 || n_radii > kBqMaxR || point_stride < 3) return V3D_ERR_INVALID_ARGUMENT;
+  if (!row_offsets && N <= 0) return V3D_ERR_INVALID_ARGUMENT;
+  BqArgs A;
+  for (int r = 0; r < kBqMaxR; r++) {
+    const int s = r < n_radii ? r : 0;
+    if (nsamples_host[s] <= 0 || !idx_host[s]) return V3D_ERR_INVALID_ARGUMENT;
+    A.r2[r] = radii_host[s] * radii_host[s];
+    A.ns[r] = nsamples_host[s];
+    A.out[r] = idx_host[s];
+  }
+  dim3 grid(ceil_div(M, kBqWarps), B);
+  cudaStream_t st = as_stream(stream);
+  switch (n_radii) {
+    case 1: ball_query_warp_kernel<1><<<grid, kBqWarps * 32, 0, st>>>(xyz, point_stride, N, row_offsets, new_xyz, M, A); break;
+    case 2: ball_query_warp_kernel<2><<<grid, kBqWarps * 32, 0, st>>>(xyz, point_stride, N, row_offsets, new_xyz, M, A); break;
+    case 3: ball_query_warp_kernel<3><<<grid, kBqWarps * 32, 0, st>>>(xyz, point_stride, N, row_offsets, new_xyz, M, A); break;
+    default: ball_query_warp_kernel<4><<<grid, kBqWarps * 32, 0, st>>>(xyz, point_stride, N, row_offsets, new_xyz, M, A); break;
+  }
+  return check_launch();
+}
+
+extern "C" int v3d_query_and_group_rows(const float* xyz, int xyz_stride, const float* feat, int feat_stride, int C, int N,
+                                        const int* row_offsets, const float* new_xyz, const int* idx, int B, int M,
+                                        int nsample, float* out, v3d_stream_t stream) {
+  if (!xyz || !new_xyz || !idx || !out || B <= 0 || B > 65535 || M <= 0 || nsample <= 0 || xyz_stride < 3 || C < 0)
+    return V3D_ERR_INVALID_ARGUMENT;
+  if (C > 0 && (!feat || feat_stride < C)) return V3D_ERR_INVALID_ARGUMENT;
+  if (!row_offsets && N <= 0) return V3D_ERR_INVALID_ARGUMENT;
+  query_group_rows_kernel<<<dim3(ceil_div(M * nsample, 256), B), 256, 0, as_stream(stream)>>>(
+      xyz, xyz_stride, feat, feat_stride, C, N, row_offsets, new_xyz, idx, M, nsample, out);
+  return check_launch();
+}
+
+extern "C" int v3d_batch_offsets(const int* indices, const int* n_rows, int capacity_rows, int B, int* offsets,
+                                 v3d_stream_t stream) {
+  if (!indices || !n_rows || !offsets || B <= 0 || capacity_rows < 0) return V3D_ERR_INVALID_ARGUMENT;
+  batch_offsets_kernel<<<ceil_div(B + 1, 128), 128, 0, as_stream(stream)>>>(reinterpret_cast<const int4*>(indices), n_rows,
+                                                                          capacity_rows, B, offsets);
+  return check_launch();
+}
+
+extern "C" int v3d_to_global(const int* indices, const int* n_rows, int capacity_rows, const float* voxel_size_host,
+                             const float* offset_host, float* xyz, v3d_stream_t stream) {
+  if (!indices || !n_rows || !voxel_size_host || !offset_host || !xyz || capacity_rows <= 0) return V3D_ERR_INVALID_ARGUMENT;
+  const int want = ceil_div(capacity_rows, 256), cap_blocks = kNumSMs * 8;
+  to_global_kernel<<<want < cap_blocks ? want : cap_blocks, 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const int4*>(indices), n_rows, capacity_rows,
+      make_float3(voxel_size_host[0], voxel_size_host[1], voxel_size_host[2]),
+      make_float3(offset_host[0], offset_host[1], offset_host[2]), xyz);
+  return check_launch();
+}
+
+extern "C" int v3d_pad_batch(const float* src, int C, const int* row_offsets, int B, int frame_capacity,
+                             unsigned long long seed, float* out, v3d_stream_t stream) {
+  if (!src || !row_offsets || !out || C <= 0 || B <= 0 || B > 65535 || frame_capacity <= 0) return V3D_ERR_INVALID_ARGUMENT;
+  const long long total = (long long)frame_capacity * C;
+  const long long want = (total + 255) / 256;
+  const int blocks = (int)(want < kNumSMs * 4 ? want : kNumSMs * 4);
+  pad_batch_kernel<<<dim3(blocks, B), 256, 0, as_stream(stream)>>>(src, C, row_offsets, frame_capacity, seed, out);
   return check_launch();
 }

@@ -131,6 +131,7 @@ struct ConvWs {
   unsigned int* uniq;    // reserved (was: append list of marked cells; the bitmap is enumerated instead)
   int* n_uniq;           // reserved
   size_t n_words, n_l1, n_l2;
+  int cap;            // row capacity of the level this workspace indexes (ranks >= cap are overflow rows)
   size_t zero_bytes;  // prefix of the workspace that must be zeroed per call
   size_t total;
 };
@@ -141,6 +142,7 @@ inline ConvWs conv_layout(void* base, unsigned long long cells, int out_capacity
   w.n_words = (size_t)((cells + 31) / 32);
   w.n_l1 = (size_t)((cells + kCoarse - 1) / kCoarse);
   w.n_l2 = (w.n_l1 + 1023) / 1024;
+  w.cap = out_capacity;
   size_t off = 0;
   w.bitmap = reinterpret_cast<unsigned int*>(p + off);
   off = align_up(off + 4 * (w.n_l1 * kWordsPerCoarse), 256);  // whole sectors
@@ -230,7 +232,10 @@ __device__ __forceinline__ int rank_of_cell(const ConvWs& W, unsigned int cell) 
   const unsigned int g1 = cell / kCoarse;
   int rank = __ldg(&W.l2[g1 >> 10]) + __ldg(&W.l1[g1]) + __popc(word & (bit - 1u));
   for (unsigned int w = g1 * kWordsPerCoarse; w < wq; w++) rank += __popc(__ldg(&W.bitmap[w]));
-  return rank;
+  // A level that overflowed its row capacity has cells whose rank is >= cap: those rows do not exist in the
+  // feature / index / rule buffers (the producers clamp), so they must read as "no neighbour" here. The overflow
+  // itself is reported through the un-clamped n_out counter (SecondEngine.finalize raises on it).
+  return rank < W.cap ? rank : -1;
 }
 
 // Output rows in ascending flat order: one thread per bitmap word walks its set bits; the row number of the

@@ -124,11 +124,11 @@ int launch_simt(const float* feat, const float* weight, const int* nbr, int nbr_
   using C = SimtCfg<COUT>;
   const size_t smem = sizeof(float) * ((size_t)Cin * C::kRows + (size_t)Cin * COUT) + sizeof(int) * C::kRows;
   if (smem > 200 * 1024) return V3D_ERR_INVALID_ARGUMENT;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.needed()) {
     V3D_CUDA_TRY(cudaFuncSetAttribute(sparse_conv_simt_kernel<COUT>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+    attr_once.done();
   }
   const int tiles_cap = ceil_div(out_cap, C::kRows);
   const int grid = tiles_cap < kNumSMs * 2 ? (tiles_cap > 0 ? tiles_cap : 1) : kNumSMs * 2;

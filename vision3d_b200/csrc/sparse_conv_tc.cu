@@ -500,9 +500,9 @@ int launch_tc(const unsigned char* feat, const unsigned char* wprep, const int* 
               int out_cap, int KV, const float* scale, const float* shift, int relu, float* out,
               unsigned char* out_packed, cudaStream_t st) {
   using C = TcCfg<CIN, COUT>;
-  static bool attr_set = false;
+  static PerDeviceOnce attr_once;
   static int fetch_warps = 8, bypass_l1 = 0;
-  if (!attr_set) {
+  if (attr_once.needed()) {
     V3D_CUDA_TRY(cudaFuncSetAttribute(sparse_conv_tc_kernel<CIN, COUT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)C::kSmemBytes));
     V3D_CUDA_TRY(cudaFuncSetAttribute(sparse_conv_tc_kernel<CIN, COUT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -511,7 +511,7 @@ int launch_tc(const unsigned char* feat, const unsigned char* wprep, const int* 
                                       (int)C::kSmemBytes));
     if (const char* e = getenv("V3D_TC_FETCH_WARPS")) fetch_warps = atoi(e);  // tuning knobs: 4, 8 or 16
     if (const char* e = getenv("V3D_TC_BYPASS_L1")) bypass_l1 = atoi(e);
-    attr_set = true;
+    attr_once.done();
   }
   const int tiles_cap = ceil_div(out_cap, kTileM);
   const int grid = tiles_cap < kNumSMs ? (tiles_cap > 0 ? tiles_cap : 1) : kNumSMs;

@@ -582,11 +582,11 @@ extern "C" int v3d_voxelize_batch(const float* points, int total_points, int max
     const size_t smem = (size_t)2048 * ppt * sizeof(VSlot) + (size_t)kVT * ppt * sizeof(unsigned int);
 #define V3D_VOX_CLUSTER(PPT, VEC)                                                                               \
   do {                                                                                                            \
-    static bool attr_set = false;                                                                                 \
-    if (!attr_set) {                                                                                              \
+    static PerDeviceOnce attr_once;                                                                                 \
+    if (attr_once.needed()) {                                                                                              \
       V3D_CUDA_TRY(cudaFuncSetAttribute(vox_cluster_kernel<PPT, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                         (int)(2048 * PPT * sizeof(VSlot) + kVT * PPT * sizeof(unsigned int))));  \
-      attr_set = true;                                                                                            \
+      attr_once.done();                                                                                            \
     }                                                                                                             \
     vox_cluster_kernel<PPT, VEC><<<B * kVC, kVT, smem, st>>>(points, frame_offsets, P, chdr, W.frame_m, voxels,   \
                                                              coords, num_points, voxel_offsets, cmean);           \

@@ -460,6 +460,110 @@ def query_and_group(xyz, new_xyz, features, idx):
     return out
 
 
+def fps_keypoints(points, npoint, idx=None, keypoints=None):
+    """PV_RCNN.sample_keypoints (detector/model.py:46-56) in one kernel: points (B, N, 3 or 4) -> (idx (B, m) int32,
+    keypoints (B, m, 3)). Rows of 4 floats (x, y, z, intensity) are read with 128-bit loads; no xyz slice copy,
+    no transposes, no separate gather_operation."""
+    x = _cuda_f32(points, "points")
+    if x.dim() != 3 or x.shape[-1] not in (3, 4):
+        raise V3DError("points must be (B, N, 3) or (B, N, 4)")
+    B, N, S = x.shape
+    m = int(npoint)
+    if idx is None:
+        idx = torch.empty((B, m), dtype=_I32, device=x.device)
+    if keypoints is None:
+        keypoints = torch.empty((B, m, 3), dtype=_F32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.load().v3d_fps_keypoints(x.data_ptr(), S, B, N, m, idx.data_ptr(), keypoints.data_ptr(), _stream()),
+              "v3d_fps_keypoints")
+    return idx, keypoints
+
+
+def ball_query_msg(radii, nsamples, xyz, new_xyz, row_offsets=None, out=None):
+    """All ball queries of one PointnetSAModuleMSG in one pass. xyz: dense (B, N, S>=3) or, with `row_offsets`
+    (B+1 int32 device), packed (rows, S) ragged sources (indices relative to the frame start). new_xyz (B, M, 3).
+    Returns [idx_r (B, M, ns_r) int32 ...]."""
+    x = _cuda_f32(xyz, "xyz")
+    q = _cuda_f32(new_xyz, "new_xyz", 3)
+    B, M, _ = q.shape
+    S = x.shape[-1]
+    N = x.shape[1] if row_offsets is None else 0
+    R = len(radii)
+    if out is None:
+        out = [torch.empty((B, M, int(ns)), dtype=_I32, device=x.device) for ns in nsamples]
+    rad = (ctypes.c_float * R)(*[float(r) for r in radii])
+    nsa = (ctypes.c_int * R)(*[int(n) for n in nsamples])
+    ptrs = (ctypes.c_void_p * R)(*[o.data_ptr() for o in out])
+    with torch.cuda.device(x.device):
+        check(_lib.load().v3d_ball_query_msg(x.data_ptr(), S, row_offsets.data_ptr() if row_offsets is not None else None,
+                                             q.data_ptr(), B, N, M, R, rad, nsa, ptrs, _stream()), "v3d_ball_query_msg")
+    return out
+
+
+def query_and_group_rows(xyz, feat, new_xyz, idx, row_offsets=None, out=None):
+    """QueryAndGroup(use_xyz=True) on row-major sources: xyz (B, N, S) / (rows, S), feat (B, N, C) / (rows, C) or None
+    -> (B, 3 + C, M, ns). `feat` may be a column slice of a wider row-major tensor (e.g. points[..., 3:], the
+    intensity the reference splits off at detector/model.py:69): it is read in place through its row stride."""
+    x = _cuda_f32(xyz, "xyz")
+    q = _cuda_f32(new_xyz, "new_xyz", 3)
+    i = _cuda_i32(idx, "idx")
+    B, M, ns = i.shape
+    S = x.shape[-1]
+    N = x.shape[1] if row_offsets is None else 0
+    f, C, fs = None, 0, 0
+    if feat is not None:
+        if not feat.is_cuda or feat.dtype != _F32:
+            raise V3DError("feat must be a CUDA float32 tensor")
+        C = feat.shape[-1]
+        rows_ok = feat.stride(-1) == 1 and (feat.dim() == 2 or feat.stride(0) == feat.shape[1] * feat.stride(1))
+        f = feat if rows_ok else feat.contiguous()
+        fs = f.stride(-2)
+    if out is None:
+        out = torch.empty((B, 3 + C, M, ns), dtype=_F32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.load().v3d_query_and_group_rows(x.data_ptr(), S, f.data_ptr() if f is not None else None, fs, C, N,
+                                                   row_offsets.data_ptr() if row_offsets is not None else None,
+                                                   q.data_ptr(), i.data_ptr(), B, M, ns, out.data_ptr(), _stream()),
+              "v3d_query_and_group_rows")
+    return out
+
+
+def batch_offsets(indices, n_rows, batch_size, out=None):
+    """offsets (B+1) int32: first row of every frame of a (b,z,y,x)-ordered index list; offsets[B] = n_rows.
+    Device-side compute_pad_amounts (detector/sparse_cnn.py:107-116): no host sync."""
+    ind = _cuda_i32(indices, "indices")
+    if out is None:
+        out = torch.empty((int(batch_size) + 1,), dtype=_I32, device=ind.device)
+    with torch.cuda.device(ind.device):
+        check(_lib.load().v3d_batch_offsets(ind.data_ptr(), n_rows.data_ptr(), int(ind.shape[0]), int(batch_size),
+                                            out.data_ptr(), _stream()), "v3d_batch_offsets")
+    return out
+
+
+def to_global(indices, n_rows, voxel_size, offset, out=None):
+    """Voxel indices (rows, 4) [b,z,y,x] -> metric xyz (rows, 3) (SparseCNNBase.to_global, sparse_cnn.py:91-105)."""
+    ind = _cuda_i32(indices, "indices")
+    if out is None:
+        out = torch.empty((ind.shape[0], 3), dtype=_F32, device=ind.device)
+    with torch.cuda.device(ind.device):
+        check(_lib.load().v3d_to_global(ind.data_ptr(), n_rows.data_ptr(), int(ind.shape[0]), f3(voxel_size), f3(offset),
+                                        out.data_ptr(), _stream()), "v3d_to_global")
+    return out
+
+
+def pad_batch(src, row_offsets, batch_size, frame_capacity, seed=0, out=None):
+    """Ragged rows (rows, C) -> dense (B, frame_capacity, C), short frames filled with random duplicates of their
+    own rows (pad_batch, sparse_cnn.py:118-126; pad_for_batch, core/preprocess.py:35-45). Same seed => same picks."""
+    x = _cuda_f32(src, "src")
+    C = x.shape[1]
+    if out is None:
+        out = torch.empty((int(batch_size), int(frame_capacity), C), dtype=_F32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.load().v3d_pad_batch(x.data_ptr(), C, row_offsets.data_ptr(), int(batch_size), int(frame_capacity),
+                                        int(seed), out.data_ptr(), _stream()), "v3d_pad_batch")
+    return out
+
+
 # =============================================================================================
 # SECOND head glue (engine-internal)
 # =============================================================================================

@@ -258,11 +258,9 @@ class SecondB200(nn.Module):
         return boxes[m], b_idx[m], c_idx[m], scores[m]
 
 
-def init_for_benchmark(model, seed=0):
-    """Random weights that keep activations O(1) through the 14 sparse layers and the RPN, so that
-    synthetic runs exercise realistic score/box distributions (with the modules' default inits the
-    activations decay to ~1e-15 by the BEV map and every score ties at sigmoid(bias)). He-normal with the
-    fan-in a typical active site actually sees (~1/3 of the 27 offsets are populated)."""
+def init_for_benchmark_backbone(model, seed=0):
+    """He-normal sparse-conv weights with the fan-in a typical active site actually sees (~1/3 of the 27 offsets
+    are populated), a live classification head. Returns the generator for further draws."""
     g = torch.Generator().manual_seed(seed)
     with torch.no_grad():
         for m in model.modules():
@@ -273,17 +271,51 @@ def init_for_benchmark(model, seed=0):
             elif isinstance(m, nn.Conv2d) and m.kernel_size != (1, 1):
                 fan = m.in_channels * m.kernel_size[0] * m.kernel_size[1]
                 m.weight.copy_(torch.randn(m.weight.shape, generator=g) * math.sqrt(2.0 / fan))
-        model.rpn.up_block[0].weight.copy_(torch.randn(model.rpn.up_block[0].weight.shape, generator=g)
-                                           * math.sqrt(2.0 / 128))
+        if hasattr(model, "rpn"):
+            model.rpn.up_block[0].weight.copy_(torch.randn(model.rpn.up_block[0].weight.shape, generator=g)
+                                               * math.sqrt(2.0 / 128))
         model.head.conv_cls.weight.copy_(torch.randn(model.head.conv_cls.weight.shape, generator=g) * 0.05)
         model.head.conv_cls.bias.fill_(-2.0)
         model.head.conv_reg.weight.copy_(torch.randn(model.head.conv_reg.weight.shape, generator=g) * 0.01)
+    return g
+
+
+def init_for_benchmark(model, seed=0):
+    """Random weights that keep activations O(1) through the 14 sparse layers and the RPN, so that
+    synthetic runs exercise realistic score/box distributions (with the modules' default inits the
+    activations decay to ~1e-15 by the BEV map and every score ties at sigmoid(bias))."""
+    init_for_benchmark_backbone(model, seed)
     return model
 
 
 # ---------------------------------------------------------------------------------------------------
 # the production engine
 # ---------------------------------------------------------------------------------------------------
+PTS_PER_FRAME = 16384
+
+# The two SECOND workloads bench.py measures (SURVEY 8d / BASELINE.json configs). bench.py and the parity tests
+# of the benchmarked configuration (tests/test_gpu_bench_config.py) both build their engine through
+# make_bench_engine, so the flags that were parity-tested are by construction the flags that were measured.
+BENCH_WORKLOADS = {
+    # target line "SECOND at batch 16": car-only (configs/second/car.yaml), 16 frames per GPU (weak scaling)
+    "t16": dict(cfg="car", frames_per_gpu=16, global_batch=None),
+    # BASELINE config 5: 3-class defaults (core/config.py), global batch 64 sharded over the ranks (strong scaling)
+    "c5": dict(cfg="three", frames_per_gpu=None, global_batch=64),
+}
+BENCH_ENGINE_FLAGS = dict(use_graph=True, tensor_cores=True, rpn_mode="fused_nhwc", fused_head=True, grouped_nms=True)
+
+
+def make_bench_engine(workload, frames, device, seed=0, **overrides):
+    """Engine + model exactly as bench.py builds them for `workload` with `frames` frames on this GPU."""
+    w = BENCH_WORKLOADS[workload]
+    cfg = car_config() if w["cfg"] == "car" else three_class_config()
+    model = init_for_benchmark(SecondB200(cfg), seed)
+    flags = dict(BENCH_ENGINE_FLAGS)
+    flags.update(overrides)
+    eng = SecondEngine(model, frames, frames * PTS_PER_FRAME, device, **flags).capture()
+    return eng, model, cfg
+
+
 # default active-site capacities per frame and level (synthetic KITTI clouds measure
 # ~14k / 27k / 20k / 9.4k / 8.2k; level 4 can never exceed 2*200*176 cells)
 DEFAULT_LEVEL_CAPS = [None, 48000, 40000, 24000, 24000]
@@ -299,9 +331,13 @@ def _fold_bn(bn):
 class SecondEngine:
     def __init__(self, model: SecondB200, batch_size: int, points_capacity: int, device, level_caps=None,
                  use_graph=True, cap_policy=0, frame_points_capacity=None, tensor_cores=True, rpn_mode="fused",
-                 fused_head=True, grouped_nms=True):
+                 fused_head=True, grouped_nms=True, keep_level_features=False):
+        """rpn_mode: "module" | "fused" | "fused_nhwc" (SECOND, detector/second.py:49-94) or "none" (PV_RCNN feeds the
+        BEV map straight to the proposal layer, detector/model.py:79-80). keep_level_features: the strided convs
+        entering levels 1-3 also write fp32 rows (PV_RCNN's cnn returns every level, sparse_cnn.py:135-146)."""
         cfg = model.cfg
         self.grouped_nms = bool(grouped_nms)
+        self.keep_level_features = bool(keep_level_features)
         self.cfg, self.B, self.P = cfg, int(batch_size), int(points_capacity)
         self.dev = torch.device(device)
         self.model = model.to(self.dev).eval()
@@ -409,7 +445,7 @@ class SecondEngine:
         # over the 288 MB activations); "fused_nhwc" = same in channels_last.
         self.rpn_mode = rpn_mode
         self.rpn_folded = []
-        if rpn_mode != "module":
+        if rpn_mode not in ("module", "none"):
             seq = list(self.model.rpn.down_block) + list(self.model.rpn.up_block)
             pad = 0
             for i, m in enumerate(seq):
@@ -479,9 +515,11 @@ class SecondEngine:
                     x = xp
                 outp = self.featp[lv_out][buf]
                 assert outp.data_ptr() != x.data_ptr()
+                both = self.keep_level_features and d["kind"] == "conv" and not last  # fp32 AND packed rows
                 plan.append((name, 1, (lambda x=x: ops.sparse_conv(
                     x, d["w"], nbr, n_rows_out, cap_out, d["scale"], d["shift"], True,
-                    out=out32 if last else None, out_packed=None if last else outp, write_f32=last))))
+                    out=out32 if (last or both) else None, out_packed=None if last else outp,
+                    write_f32=last or both))))
                 return out32 if last else outp
 
             while self.layers[li]["kind"] == "subm":
@@ -497,7 +535,7 @@ class SecondEngine:
             x = conv_op("sconv_L%d_%dx%d" % (lv, d["cin"], d["cout"]), d, x, self.nbr_conv[lv], self.n_rows[lv + 1],
                         self.caps[lv + 1], lv + 1, 0, li == len(self.layers) - 1)
             li += 1
-        if self.rpn_mode == "fused_nhwc":
+        if self.rpn_mode in ("fused_nhwc", "none"):
             # BEV map written directly in channels_last memory (what cuDNN's sm_100 kernels consume)
             sh = self.shapes[4]
             self.bev_nhwc = torch.empty((B, 64 * sh[0], sh[1], sh[2]), dtype=torch.float32, device=self.dev,
@@ -509,8 +547,12 @@ class SecondEngine:
             plan.append(("dense", 2, (lambda x=x: ops.sparse_to_dense(
                 x, self.indices[4], self.n_rows[4], self.caps[4], B, self.shapes[4], self.dense_out,
                 self.dense_ws))))
-        plan.append(("rpn(cudnn)", 0, self._rpn))
-        native_head = self.fused_head and self.rpn_mode == "fused_nhwc"  # logits, top-k, reg gather, decode
+        self.n_backbone_ops = len(plan)  # plan[:n_backbone_ops] = raw points -> dense BEV (all v3d kernels)
+        if self.rpn_mode != "none":
+            plan.append(("rpn(cudnn)", 0, self._rpn))
+        else:
+            self._fmap = self.bev_nhwc
+        native_head = self.fused_head and self.rpn_mode in ("fused_nhwc", "none")  # logits, top-k, reg gather, decode
         plan.append(("heads+topk+decode" if native_head else "heads+topk(torch)+decode",
                      5 if native_head else (1 if self.fused_head else 0), self._head))
         plan.append(("nms_rotated", 4 if (self.grouped_nms and cfg.TOPK <= 128) else 3, self._nms))
@@ -520,7 +562,7 @@ class SecondEngine:
 
     def _rpn(self):
         B = self.B
-        if self.rpn_mode == "fused_nhwc":
+        if self.rpn_mode in ("fused_nhwc", "none"):
             x = self.bev_nhwc
         else:
             x = self.dense_out.view(B, 64 * self.shapes[4][0], self.shapes[4][1], self.shapes[4][2])
