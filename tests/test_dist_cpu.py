@@ -31,6 +31,11 @@ def _worker(rank, world, port, ret):
     res[n, 0] = k
     g = vdist.gather_results(res)
     assert g.shape == (world, n + 1, 11)
+    # in-place form bench.py uses: this rank's result lives in its slot of the gather buffer
+    buf = torch.zeros((world, n + 1, 11))
+    buf[rank].copy_(res)
+    g2 = vdist.gather_results(buf[rank], buf)
+    assert g2.data_ptr() == buf.data_ptr() and torch.equal(g2, g)
     boxes, bidx, cidx, scores = vdist.unpack_global(g.numpy(), hi - lo)
     ret[rank] = (lo, hi, boxes[:, 0].tolist(), bidx.tolist(), cidx.tolist())
     dist.barrier()

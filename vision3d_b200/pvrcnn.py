@@ -262,31 +262,37 @@ class KeypointStage:
             x = F.relu(F.conv2d(x, w[:, :, None, None], b), inplace=True)
         return x.amax(dim=3)
 
-    def _sa(self, i):
-        cfg = self.cfg
-        xyz, feat, offs = self._source(i)
-        pn = self.model.pnets[i]
-        radii = [g.radius for g in pn.groupers]
-        ops.ball_query_msg(radii, cfg.SAMPLES_PN, xyz, self.keypoints, offs, out=self.sa_idx[i])
-        c0 = 0
-        for r, idx in enumerate(self.sa_idx[i]):
-            g = ops.query_and_group_rows(xyz, feat, self.keypoints, idx, offs)
-            o = self._mlp_max(g, self.sa_mlps[i][r])
-            self.kp_features[:, self._sa_c0[i] + c0: self._sa_c0[i] + c0 + o.shape[1]] = o
-            c0 += o.shape[1]
+    # every set-abstraction module is three plan ops (so that bench.py can time a9 / a10 / the MLP separately):
+    # all ball queries of the module, then per radius the grouping and the shared MLP + max
+    def _sa_query(self, i):
+        xyz, _, offs = self._source(i)
+        radii = [g.radius for g in self.model.pnets[i].groupers]
+        ops.ball_query_msg(radii, self.cfg.SAMPLES_PN, xyz, self.keypoints, offs, out=self.sa_idx[i])
 
-    def _roi(self):
-        cfg = self.cfg
-        B, n, m = self.B, self.n, cfg.GRIDPOOL_NUM_GRIDPOINTS
-        grid = self.gridpoints
+    def _sa_group(self, i, r):
+        xyz, feat, offs = self._source(i)
+        self._grouped = ops.query_and_group_rows(xyz, feat, self.keypoints, self.sa_idx[i][r], offs)
+
+    def _sa_mlp(self, i, r):
+        o = self._mlp_max(self._grouped, self.sa_mlps[i][r])
+        c0 = self._sa_c0[i] + sum(m[-1][0].shape[0] for m in self.sa_mlps[i][:r])
+        self.kp_features[:, c0:c0 + o.shape[1]] = o
+
+    def _roi_query(self):
         pn = self.model.roi_grid_pool.pnet
-        ops.ball_query_msg([g.radius for g in pn.groupers], cfg.SAMPLES_PN, self.keypoints, grid, None, out=self.roi_idx)
-        outs = []
-        for r, idx in enumerate(self.roi_idx):
-            g = ops.query_and_group(self.keypoints, grid, self.kp_features, idx)        # (B, 515, n*16, ns)
-            outs.append(self._mlp_max(g, self.roi_mlps[r]))
-        f = torch.cat(outs, 1)                                                          # (B, 192, n*16)
-        f = f.view(B, -1, n, m).permute(0, 2, 1, 3).contiguous().view(B, n, -1)
+        ops.ball_query_msg([g.radius for g in pn.groupers], self.cfg.SAMPLES_PN, self.keypoints, self.gridpoints, None,
+                           out=self.roi_idx)
+
+    def _roi_group(self, r):
+        self._grouped = ops.query_and_group(self.keypoints, self.gridpoints, self.kp_features, self.roi_idx[r])
+
+    def _roi_mlp(self, r):
+        self._roi_out[r] = self._mlp_max(self._grouped, self.roi_mlps[r])       # (B, 96, n*16)
+
+    def _roi_reduce(self):
+        B, n, m = self.B, self.n, self.cfg.GRIDPOOL_NUM_GRIDPOINTS
+        f = torch.cat(self._roi_out, 1)                                          # (B, 192, n*16)
+        f = f.view(B, -1, n, m).permute(0, 2, 1, 3).contiguous().view(B, n, -1)  # roi_grid_pool.py:69-70
         self.pooled = self.model.roi_grid_pool.reduction(f)
 
     def _levels(self):
@@ -308,9 +314,17 @@ class KeypointStage:
             plan.append(("backbone/" + name, fn))
         plan.append(("offsets+to_global", self._levels))
         for i in range(5):
-            plan.append(("sa%d(ball_query+group+mlp+max)" % i, (lambda i=i: self._sa(i))))
-        plan.append(("bev_gather", self._bev))
-        plan.append(("roi_grid_pool", self._roi))
+            plan.append(("sa%d/ball_query" % i, (lambda i=i: self._sa_query(i))))
+            for r in range(len(self.cfg.SAMPLES_PN)):
+                plan.append(("sa%d/group_r%d" % (i, r), (lambda i=i, r=r: self._sa_group(i, r))))
+                plan.append(("sa%d/mlp+max_r%d(torch)" % (i, r), (lambda i=i, r=r: self._sa_mlp(i, r))))
+        plan.append(("bev_gather(torch)", self._bev))
+        plan.append(("roi/ball_query", self._roi_query))
+        self._roi_out = [None] * len(self.cfg.SAMPLES_PN)
+        for r in range(len(self.cfg.SAMPLES_PN)):
+            plan.append(("roi/group_r%d" % r, (lambda r=r: self._roi_group(r))))
+            plan.append(("roi/mlp+max_r%d(torch)" % r, (lambda r=r: self._roi_mlp(r))))
+        plan.append(("roi/reduction_mlp(torch)", self._roi_reduce))
         self.plan = plan
 
     def load(self, clouds, gridpoints):

@@ -331,10 +331,13 @@ def _fold_bn(bn):
 class SecondEngine:
     def __init__(self, model: SecondB200, batch_size: int, points_capacity: int, device, level_caps=None,
                  use_graph=True, cap_policy=0, frame_points_capacity=None, tensor_cores=True, rpn_mode="fused",
-                 fused_head=True, grouped_nms=True, keep_level_features=False):
+                 fused_head=True, grouped_nms=True, keep_level_features=False, result_out=None, post_step=None):
         """rpn_mode: "module" | "fused" | "fused_nhwc" (SECOND, detector/second.py:49-94) or "none" (PV_RCNN feeds the
         BEV map straight to the proposal layer, detector/model.py:79-80). keep_level_features: the strided convs
-        entering levels 1-3 also write fp32 rows (PV_RCNN's cnn returns every level, sparse_cnn.py:135-146)."""
+        entering levels 1-3 also write fp32 rows (PV_RCNN's cnn returns every level, sparse_cnn.py:135-146).
+        result_out: external (N+1, 11) f32 buffer the packed detections are written to (multi-GPU: this rank's slot
+        of the all-gather buffer, so the collective runs in place); post_step: callable issued at the end of every
+        step, INSIDE the captured graph (the all-gather of SURVEY 8e)."""
         cfg = model.cfg
         self.grouped_nms = bool(grouped_nms)
         self.keep_level_features = bool(keep_level_features)
@@ -418,7 +421,13 @@ class SecondEngine:
         self.bev_cols = torch.tensor([0, 1, 3, 4, 6], device=dev)  # x, y, w, l, yaw (proposal.py:52)
         self.row_ids = torch.arange(self.N, device=dev)
         # packed result: 7 box + score + batch + class + valid, then one row of counters
-        self.result = torch.zeros((self.N + 1, 11), dtype=torch.float32, device=dev)
+        if result_out is not None:
+            assert tuple(result_out.shape) == (self.N + 1, 11) and result_out.is_contiguous() and \
+                result_out.dtype == torch.float32 and result_out.device == dev
+            self.result = result_out
+        else:
+            self.result = torch.zeros((self.N + 1, 11), dtype=torch.float32, device=dev)
+        self.post_step = post_step
         self.h_result = torch.zeros((self.N + 1, 11), dtype=torch.float32).pin_memory()
         self.graph = None
         # ---- head glue: one decode kernel + one pack kernel instead of ~55 tiny torch launches
@@ -557,6 +566,8 @@ class SecondEngine:
                      5 if native_head else (1 if self.fused_head else 0), self._head))
         plan.append(("nms_rotated", 4 if (self.grouped_nms and cfg.TOPK <= 128) else 3, self._nms))
         plan.append(("pack_result", 1 if self.fused_head else 0, self._pack))
+        if self.post_step is not None:
+            plan.append(("allgather(nccl)", 0, self.post_step))
         self.plan = plan
         self.kernel_launches = sum(p[1] for p in plan)
 
