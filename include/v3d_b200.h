@@ -88,6 +88,15 @@ V3D_API int v3d_nms_rotated_grouped(const float* dets, const float* scores, int 
                                     float iou_threshold, int64_t* keep, int* num_keep, void* workspace,
                                     size_t workspace_bytes, v3d_stream_t stream);
 
+/* Training-side consumer of a13: ProposalTargetAssigner.match_class_i (core/proposal_targets.py:53-60)
+ * = box_iou_rotated(gt[M,5], anchors[N,5]) + Matcher.__call__ (ops/matcher.py:86-107) without materialising the M x N
+ * matrix: matches[a] = first gt index of maximal IoU, labels[a] = label of the stratum [low, high) the maximum falls in
+ * (strata evaluated in order, default label 1), matched_vals[a] (optional) = that maximum. M in 1..256 (M == 0 is the
+ * reference's "no gt" shortcut, handled by the binding), strata are HOST arrays of n_strata <= 8 entries. */
+V3D_API int v3d_match_anchors(const float* gt_boxes, int M, const float* anchors, int N, int n_strata,
+                              const float* low_host, const float* high_host, const int* label_host,
+                              int64_t* matches, signed char* labels, float* matched_vals, v3d_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * a1 (+a2)  point -> voxel for a whole batch in one call
  * replaces spconv.utils.VoxelGenerator(...).generate(points) per frame and the batch-index

@@ -33,8 +33,16 @@ __device__ __forceinline__ void mma(uint32_t d, uint32_t a_tmem, uint64_t adesc,
   }
 }
 
+// bf16 SS-mode MMA with the disable-output-lane operand (4 x 32-bit lane mask)
+__device__ __forceinline__ void mma_masked(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t m0,
+                                           uint32_t m1, uint32_t m2, uint32_t m3) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%4, %5, %6, %7}, p;\n\t}" ::"r"(d),
+               "l"(adesc), "l"(bdesc), "r"(idesc), "r"(m0), "r"(m1), "r"(m2), "r"(m3)
+               : "memory");
+}
+
 template <int KIND, bool TS, int N, int REPS>
-__global__ void probe(long long* out) {
+__global__ void probe(long long* out, unsigned int mask) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ uint64_t bar;
@@ -56,10 +64,15 @@ __global__ void probe(long long* out) {
   if (threadIdx.x == 0) {
     const uint64_t bdesc = make_desc(smem_u32(base));
     const uint64_t adesc = make_desc(smem_u32(base) + 32768);
-    constexpr uint32_t idesc = make_idesc(128, N, KIND);
+    constexpr uint32_t idesc = make_idesc(128, N, KIND == 3 ? 2 : KIND);
     const long long t0 = clock64();
 #pragma unroll 8
-    for (int r = 0; r < REPS; r++) mma<KIND, TS>(tm, tm + 256 + 8 * (r & 7), adesc + 2 * (r & 3), bdesc + 2 * (r & 3), idesc);
+    for (int r = 0; r < REPS; r++) {
+      if (KIND == 3)
+        mma_masked(tm, adesc + 2 * (r & 3), bdesc + 2 * (r & 3), make_idesc(128, N, 2), mask, mask, mask, mask);
+      else
+        mma<KIND, TS>(tm, tm + 256 + 8 * (r & 7), adesc + 2 * (r & 3), bdesc + 2 * (r & 3), idesc);
+    }
     const long long t1 = clock64();
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
     uint32_t ok = 0;
@@ -75,7 +88,7 @@ __global__ void probe(long long* out) {
 }
 
 template <int KIND, bool TS, int N>
-void run(const char* name) {
+void run(const char* name, unsigned int mask = 0u) {
   constexpr int REPS = 2048;
   long long* d;
   cudaMalloc(&d, 16);
@@ -83,7 +96,7 @@ void run(const char* name) {
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
   long long h[2] = {0, 0};
   for (int it = 0; it < 2; it++) {
-    k<<<1, 128, 80 * 1024>>>(d);
+    k<<<1, 128, 80 * 1024>>>(d, mask);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
       printf("%-28s N=%3d  ERROR %s\n", name, N, cudaGetErrorString(e));
@@ -110,5 +123,11 @@ int main() {
   sweep<1, true>("f16  K=16 A=TMEM");
   sweep<1, false>("f16  K=16 A=smem");
   sweep<2, true>("bf16 K=16 A=TMEM");
+  sweep<2, false>("bf16 K=16 A=smem");
+  run<3, false, 64>("bf16 SS masked, mask=0", 0u);
+  run<3, false, 128>("bf16 SS masked, mask=0", 0u);
+  run<3, false, 64>("bf16 SS masked, half off", 0x0F0F3355u);
+  run<3, false, 128>("bf16 SS masked, half off", 0x0F0F3355u);
+  run<3, false, 128>("bf16 SS masked, all off", 0xFFFFFFFFu);
   return 0;
 }

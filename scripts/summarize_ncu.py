@@ -121,5 +121,45 @@ def traffic(path, tag=None):
     print(json.dumps(res, indent=1))
 
 
+COUNTERS = [("us", "gpu__time_duration.sum"), ("cycles", "sm__cycles_elapsed.max"),
+            ("tensor %act", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+            ("l1tex data-pipe %", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+            ("lts %", "lts__throughput.avg.pct_of_peak_sustained_elapsed"),
+            ("dram %", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+            ("L2->L1 MB", "l1tex__m_xbar2l1tex_read_bytes.sum"),
+            ("LDGSTS inst", "smsp__inst_executed_op_ldgsts.sum"),
+            ("smem wavefronts (lsu)", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"),
+            ("of which ldgsts", "smsp__sass_l1tex_data_pipe_lsu_wavefronts_mem_shared_op_ldgsts.sum"),
+            ("of which ld", "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum"),
+            ("tensor-core smem wavefronts", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum"),
+            ("L2 hit %", "lts__t_sector_hit_rate.pct")]
+
+
+def counters(path, pattern="sparse_conv_tc"):
+    """Per-launch L1TEX / L2 / tensor counters of the kernels matching `pattern` (the evidence behind DESIGN 4.1)."""
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.DictReader(io.StringIO(out[out.index('"ID"'):])))
+    units, rows = rows[0], rows[1:]
+    scale = {"Gbyte": 1e3, "Mbyte": 1.0, "Kbyte": 1e-3, "byte": 1e-6}
+    print("# ncu --set full counters per launch (%s), kernels matching '%s'\n" % (path.split("/")[-1], pattern))
+    print("| kernel | " + " | ".join(n for n, _ in COUNTERS) + " |")
+    print("|---|" + "---:|" * len(COUNTERS))
+    for r in rows:
+        if pattern not in r["Kernel Name"]:
+            continue
+        vals = []
+        for n, m in COUNTERS:
+            if m not in r or r[m] in ("", None):
+                vals.append("n/a")
+                continue
+            v = float(r[m].replace(",", ""))
+            if units[m] in scale:
+                v *= scale[units[m]]
+            if units[m] in ("ns", "nsecond"):
+                v /= 1e3
+            vals.append("%.1f" % v if v < 1e4 else "%.3g" % v)
+        print("| `%s` | %s |" % (short(r["Kernel Name"]), " | ".join(vals)))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])
+    {"launches": launches, "full": full, "traffic": traffic, "counters": counters}[sys.argv[1]](*sys.argv[2:])

@@ -96,3 +96,54 @@ def test_oracle_keypoint_stage_small():
     # keypoints are cloud points; every RoI ball-query index addresses a keypoint
     assert np.array_equal(st["keypoints"][1], clouds[1][st["kp_idx"][1], :3])
     assert all(int(np.stack(v).max()) < 128 for v in st["roi_idx"].values())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# training-side IoU consumer: ProposalTargetAssigner mirror pinned to the reference's own run
+# ---------------------------------------------------------------------------------------------------------------
+def _dense_targets(item):
+    G_cls, M_cls, G_reg = item["G_cls"], item["M_cls"], item["G_reg"]
+    pos = torch.nonzero(G_cls.reshape(-1) == 1).squeeze(1)
+    ign = torch.nonzero(~M_cls.reshape(-1)).squeeze(1)
+    return pos.numpy(), ign.numpy(), G_reg.reshape(-1, 7)[pos].numpy(), int(item["M_reg"].sum())
+
+
+def test_target_assigner_mirror_matches_reference_golden():
+    """targets.ProposalTargetAssignerB200 (reference expression path, IoU = the oracle's restatement of the reference
+    CPU op) reproduces the reference's own ProposalTargetAssigner.forward: positives, ignored anchors, matched boxes and
+    encoded regression targets (tests/golden/make_targets_golden.py)."""
+    from vision3d_b200 import second, targets
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "targets_golden.npz"))
+    cfg = second.three_class_config()
+
+    def iou_cpu(a, b):
+        return torch.from_numpy(oracle.box_iou_rotated(a.numpy(), b.numpy(), 0))   # variant 0 = reference CPU build
+
+    assigner = targets.ProposalTargetAssignerB200(cfg, fused=False, iou_fn=iou_cpu)
+    for tag in ("a", "b"):
+        item = dict(boxes=torch.from_numpy(gold[tag + "_boxes"]), class_idx=torch.from_numpy(gold[tag + "_class_idx"]))
+        with torch.no_grad():
+            assigner(item)
+        assert tuple(item["G_cls"].shape) == tuple(gold[tag + "_shape"])
+        pos, ign, reg, n_reg = _dense_targets(item)
+        assert np.array_equal(pos, gold[tag + "_pos"]) and np.array_equal(ign, gold[tag + "_ign"])
+        assert n_reg == int(gold[tag + "_n_reg_mask"])
+        np.testing.assert_allclose(reg, gold[tag + "_reg_pos"], rtol=0, atol=1e-6)
+        box_idx, _ = assigner.match_all_classes(item["boxes"], item["class_idx"])
+        assert np.array_equal(box_idx.reshape(-1)[torch.from_numpy(pos)].numpy(), gold[tag + "_pos_box"])
+
+
+def test_encode_decode_roundtrip_and_matcher_strata():
+    from vision3d_b200 import second, targets
+    g = torch.Generator().manual_seed(0)
+    anchors = second.make_anchors(second.three_class_config()).view(-1, 7)[:64]
+    boxes = anchors + torch.randn((64, 7), generator=g) * 0.1
+    boxes[:, 6] = anchors[:, 6] + torch.rand(64, generator=g) * 3.0       # encode wraps yaw differences into [0, pi)
+    back = second.decode_boxes(targets.encode_boxes(boxes, anchors), anchors)
+    assert torch.allclose(back, boxes, atol=1e-5)
+    m = targets.Matcher([0.45, 0.6], [0, -1, 1])
+    q = torch.tensor([[0.1, 0.5, 0.7, 0.45, 0.6], [0.2, 0.1, 0.0, 0.0, 0.0]])
+    matches, labels = m(q)
+    assert matches.tolist() == [1, 0, 0, 0, 0] and labels.tolist() == [0, -1, 1, -1, 1]
+    e, l = m(torch.zeros((0, 3)))
+    assert e.tolist() == [0, 0, 0] and l.tolist() == [0, 0, 0]

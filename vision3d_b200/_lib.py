@@ -23,6 +23,7 @@ SIGNATURES = {
     "v3d_nms_rotated_workspace_bytes": (c_size_t, [c_int]),
     "v3d_nms_rotated": (c_int, [P, P, c_int, c_float, P, P, P, c_size_t, P]),
     "v3d_nms_rotated_grouped": (c_int, [P, P, c_int, c_int, c_float, P, P, P, c_size_t, P]),
+    "v3d_match_anchors": (c_int, [P, c_int, P, c_int, c_int, P, P, P, P, P, P, P]),
     "v3d_voxelize_workspace_bytes": (c_size_t, [c_int, c_int]),
     "v3d_voxelize_workspace_init": (c_int, [P, c_size_t, c_int, c_int, P]),
     "v3d_voxelize_batch": (c_int, [P, c_int, c_int, c_int, P, c_int, P, P, P, c_int, c_int, c_int,

@@ -225,6 +225,50 @@ __global__ void __launch_bounds__(kIouThreads) box_iou_kernel(const float* __res
 }
 
 // -------------------------------------------------------------------------------------------
+// Training-side consumer of a13: ProposalTargetAssigner.match_class_i
+// (core/proposal_targets.py:53-60) = box_iou_rotated(M gt boxes, N anchors) followed by Matcher.__call__
+// (ops/matcher.py:86-107: max over the gt axis, threshold strata -> label). Fused: one thread per anchor walks the
+// gt boxes staged in shared memory, the M x N matrix (M x 70 400 per class) is never written.
+// Same IoU arithmetic as box_iou_kernel; max keeps the FIRST gt index on ties (what torch.max returns for the
+// row-major (M, N) matrix on CUDA); strata are evaluated in the reference's order (later strata overwrite).
+// -------------------------------------------------------------------------------------------
+constexpr int kMatchMaxGt = 256;
+constexpr int kMatchMaxStrata = 8;
+struct MatchStrata {
+  int n;
+  float low[kMatchMaxStrata], high[kMatchMaxStrata];
+  int label[kMatchMaxStrata];
+};
+
+__global__ void __launch_bounds__(256) match_anchors_kernel(const float* __restrict__ gt, int M,
+                                                            const float* __restrict__ anchors, int N, MatchStrata S,
+                                                            long long* __restrict__ matches,
+                                                            signed char* __restrict__ labels,
+                                                            float* __restrict__ matched_vals) {
+  __shared__ BoxPre g[kMatchMaxGt];
+  for (int i = threadIdx.x; i < M; i += blockDim.x) g[i] = make_pre(gt + (size_t)i * 5);
+  __syncthreads();
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= N) return;
+  const BoxPre A = make_pre(anchors + (size_t)a * 5);
+  float best = -1.0f;
+  int bi = 0;
+  for (int i = 0; i < M; i++) {
+    const float v = iou_pair(g[i], A);  // row = gt box, column = anchor: box_iou_rotated(boxes, anchors)
+    if (v > best) {
+      best = v;
+      bi = i;
+    }
+  }
+  int lab = 1;  // matcher.py:96
+  for (int t = 0; t < S.n; t++)
+    if (best >= S.low[t] && best < S.high[t]) lab = S.label[t];
+  matches[a] = bi;
+  labels[a] = (signed char)lab;
+  if (matched_vals) matched_vals[a] = best;
+}
+
+// -------------------------------------------------------------------------------------------
 // a12: NMS, three launches, nothing leaves the device.
 // -------------------------------------------------------------------------------------------
 constexpr int kTile = 64;
@@ -601,5 +645,23 @@ extern "C" int v3d_nms_rotated(const float* dets, const float* scores, int N, fl
     nms_scan_kernel<<<1, 1024, sizeof(unsigned long long) * cb, st>>>(mask, order, N, cb,
                                                                      reinterpret_cast<long long*>(keep), num_keep);
   }
+  return check_launch();
+}
+
+extern "C" int v3d_match_anchors(const float* gt_boxes, int M, const float* anchors, int N, int n_strata,
+                                 const float* low_host, const float* high_host, const int* label_host,
+                                 int64_t* matches, signed char* labels, float* matched_vals, v3d_stream_t stream) {
+  if (M <= 0 || M > kMatchMaxGt || N <= 0 || n_strata <= 0 || n_strata > kMatchMaxStrata) return V3D_ERR_INVALID_ARGUMENT;
+  if (!gt_boxes || !anchors || !low_host || !high_host || !label_host || !matches || !labels) return V3D_ERR_INVALID_ARGUMENT;
+  MatchStrata S;
+  S.n = n_strata;
+  for (int t = 0; t < n_strata; t++) {
+    S.low[t] = low_host[t];
+    S.high[t] = high_host[t];
+    S.label[t] = label_host[t];
+  }
+  match_anchors_kernel<<<ceil_div(N, 256), 256, 0, as_stream(stream)>>>(gt_boxes, M, anchors, N, S,
+                                                                        reinterpret_cast<long long*>(matches), labels,
+                                                                        matched_vals);
   return check_launch();
 }

@@ -20,11 +20,11 @@ namespace v3d {
 namespace {
 
 constexpr int kFpsCluster = 8;
-constexpr int kFpsThreads = 256;
+constexpr int kFpsThreads = 512;
 
-struct Cand {
-  float d;
-  int i;
+struct alignas(16) Cand {
+  unsigned int dbits;  // distance as ordered bits (distances are >= 0, so uint order == float order)
+  unsigned int nidx;   // ~index: larger = lower index, so max over (dbits, nidx) = farthest point, ties -> lowest index
   float x, y, z;
   float pad[3];
 };
@@ -34,9 +34,12 @@ __device__ __forceinline__ float dist2(float ax, float ay, float az, float bx, f
   return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
-// better = larger distance, ties -> smaller index
-__device__ __forceinline__ bool better(float d1, int i1, float d2, int i2) {
-  return d1 > d2 || (d1 == d2 && i1 < i2);
+// arg-max over a warp of (dbits, nidx) pairs in lexicographic order: two REDUX instructions
+__device__ __forceinline__ void warp_argmax(unsigned int& dbits, unsigned int& nidx) {
+  const unsigned int m = __reduce_max_sync(0xffffffffu, dbits);
+  const unsigned int c = __reduce_max_sync(0xffffffffu, dbits == m ? nidx : 0u);
+  dbits = m;
+  nidx = c;
 }
 
 template <int PPT>
@@ -47,11 +50,11 @@ __global__ void __cluster_dims__(kFpsCluster, 1, 1) __launch_bounds__(kFpsThread
   const int rank = (int)cluster.block_rank();
   const int b = blockIdx.x / kFpsCluster;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kWarps = kFpsThreads / 32;
   const float* P = xyz + (size_t)b * N * stride;
 
   __shared__ Cand cand[2][kFpsCluster];  // written by every CTA of the cluster through DSMEM
-  __shared__ float wd[kFpsThreads / 32];
-  __shared__ int wi[kFpsThreads / 32];
+  __shared__ unsigned int wd[2][kWarps], wi[2][kWarps];
 
   // CTA `rank` owns the contiguous slice [s0, s0 + S); thread t owns s0 + t + k*blockDim, k < PPT
   const int S = PPT * kFpsThreads;
@@ -89,95 +92,67 @@ __global__ void __cluster_dims__(kFpsCluster, 1, 1) __launch_bounds__(kFpsThread
   cluster.sync();
 
   for (int j = 1; j < m; j++) {
+    const int par = j & 1;
+    // 1. running min distance of my points to the selected set, my farthest point (lowest index on ties)
     float bd = -1.f;
-    int bi = 0x7fffffff;
-    float bx = 0.f, by = 0.f, bz = 0.f;
+    int bk = 0;
 #pragma unroll
     for (int k = 0; k < PPT; k++) {
       const float d = dist2(px[k], py[k], pz[k], cx, cy, cz);
-      const float d2 = md[k] < 0.f ? -1.f : fminf(d, md[k]);
+      const float d2 = fminf(d, md[k]);  // md = -1 (no point) stays -1
       md[k] = d2;
       if (d2 > bd) {  // ascending index inside the thread: strict > keeps the lowest index
         bd = d2;
-        bi = s0 + tid + k * kFpsThreads;
-        bx = px[k];
-        by = py[k];
-        bz = pz[k];
+        bk = k;
       }
     }
-    // warp arg-max
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      const float od = __shfl_xor_sync(0xffffffffu, bd, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      const float ox = __shfl_xor_sync(0xffffffffu, bx, o);
-      const float oy = __shfl_xor_sync(0xffffffffu, by, o);
-      const float oz = __shfl_xor_sync(0xffffffffu, bz, o);
-      if (better(od, oi, bd, bi)) {
-        bd = od;
-        bi = oi;
-        bx = ox;
-        by = oy;
-        bz = oz;
-      }
-    }
-    __shared__ float wx[kFpsThreads / 32], wy[kFpsThreads / 32], wz[kFpsThreads / 32];
+    const unsigned int my_d = bd < 0.f ? 0u : __float_as_uint(bd);
+    const unsigned int my_n = bd < 0.f ? 0u : ~(unsigned int)(s0 + tid + bk * kFpsThreads);
+    // 2. warp arg-max (2 REDUX), warp leaders publish, every warp reduces the kWarps candidates redundantly
+    unsigned int d = my_d, n = my_n;
+    warp_argmax(d, n);
     if (lane == 0) {
-      wd[warp] = bd;
-      wi[warp] = bi;
-      wx[warp] = bx;
-      wy[warp] = by;
-      wz[warp] = bz;
+      wd[par][warp] = d;
+      wi[par][warp] = n;
     }
     __syncthreads();
-    const int par = j & 1;
-    if (warp == 0) {
-      float d = lane < kFpsThreads / 32 ? wd[lane] : -2.f;
-      int i = lane < kFpsThreads / 32 ? wi[lane] : 0x7fffffff;
-      float x = lane < kFpsThreads / 32 ? wx[lane] : 0.f;
-      float y = lane < kFpsThreads / 32 ? wy[lane] : 0.f;
-      float z = lane < kFpsThreads / 32 ? wz[lane] : 0.f;
+    d = lane < kWarps ? wd[par][lane] : 0u;
+    n = lane < kWarps ? wi[par][lane] : 0u;
+    warp_argmax(d, n);
+    // 3. the thread that owns the CTA's winner delivers it (with its coordinates) to all CTAs of the cluster
+    if (d == my_d && n == my_n && bd >= 0.f) {
+      float wx = px[0], wy = py[0], wz = pz[0];
 #pragma unroll
-      for (int o = 4; o; o >>= 1) {
-        const float od = __shfl_xor_sync(0xffffffffu, d, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, i, o);
-        const float ox = __shfl_xor_sync(0xffffffffu, x, o);
-        const float oy = __shfl_xor_sync(0xffffffffu, y, o);
-        const float oz = __shfl_xor_sync(0xffffffffu, z, o);
-        if (better(od, oi, d, i)) {
-          d = od;
-          i = oi;
-          x = ox;
-          y = oy;
-          z = oz;
+      for (int k = 1; k < PPT; k++)
+        if (bk == k) {
+          wx = px[k];
+          wy = py[k];
+          wz = pz[k];
         }
+#pragma unroll
+      for (int r = 0; r < kFpsCluster; r++) {
+        Cand* remote = cluster.map_shared_rank(&cand[par][rank], r);
+        *reinterpret_cast<uint4*>(remote) = make_uint4(d, n, __float_as_uint(wx), __float_as_uint(wy));
+        remote->z = wz;
       }
-      // lanes 0..7 each deliver this CTA's candidate to one CTA of the cluster
-      d = __shfl_sync(0xffffffffu, d, 0);
-      i = __shfl_sync(0xffffffffu, i, 0);
-      x = __shfl_sync(0xffffffffu, x, 0);
-      y = __shfl_sync(0xffffffffu, y, 0);
-      z = __shfl_sync(0xffffffffu, z, 0);
-      if (lane < kFpsCluster) {
-        Cand* remote = cluster.map_shared_rank(&cand[par][rank], lane);
-        remote->d = d;
-        remote->i = i;
-        remote->x = x;
-        remote->y = y;
-        remote->z = z;
+    } else if (d == 0u && n == 0u && tid == 0) {  // this CTA holds no point at all (N < s0): deliver "nothing"
+#pragma unroll
+      for (int r = 0; r < kFpsCluster; r++) {
+        Cand* remote = cluster.map_shared_rank(&cand[par][rank], r);
+        *reinterpret_cast<uint4*>(remote) = make_uint4(0u, 0u, 0u, 0u);
+        remote->z = 0.f;
       }
     }
-    cluster.sync();  // candidates of step j visible everywhere; parity buffers make one sync enough
-    float gd = cand[par][0].d;
-    int gi = cand[par][0].i;
+    cluster.sync();  // candidates of step j visible everywhere; parity buffers make one sync per step enough
+    // 4. cluster arg-max over the 8 candidates (every thread, broadcast reads)
+    unsigned int gd = cand[par][0].dbits, gn = cand[par][0].nidx;
     int gr = 0;
 #pragma unroll
     for (int r = 1; r < kFpsCluster; r++) {
-      const float d = cand[par][r].d;
-      const int i = cand[par][r].i;
-      if (better(d, i, gd, gi)) {
-        gd = d;
-        gi = i;
+      const unsigned int rd = cand[par][r].dbits, rn = cand[par][r].nidx;
+      if (rd > gd || (rd == gd && rn > gn)) {
+        gd = rd;
+        gn = rn;
         gr = r;
       }
     }
@@ -185,7 +160,7 @@ __global__ void __cluster_dims__(kFpsCluster, 1, 1) __launch_bounds__(kFpsThread
     cy = cand[par][gr].y;
     cz = cand[par][gr].z;
     if (rank == 0 && tid == 0) {
-      out[(size_t)b * m + j] = gi;
+      out[(size_t)b * m + j] = (int)~gn;
       if (out_xyz) {
         float* o = out_xyz + ((size_t)b * m + j) * 3;
         o[0] = cx;

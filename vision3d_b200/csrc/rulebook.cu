@@ -279,36 +279,88 @@ __global__ void __launch_bounds__(256) conv_rank_kernel(ConvWs W, ConvGeom G, in
   }
 }
 
+// set cells before `cell` in flat order (two-level prefix + the earlier words of the cell's 32-byte sector, read as two
+// 128-bit loads); `word` = the bitmap word of the cell (already loaded by the caller)
+__device__ __forceinline__ int rank_before(const ConvWs& W, unsigned int cell, unsigned int word) {
+  const unsigned int wq = cell >> 5, g1 = cell / kCoarse, wi = wq & (kWordsPerCoarse - 1);
+  int rank = __ldg(&W.l2[g1 >> 10]) + __ldg(&W.l1[g1]) + __popc(word & ((1u << (cell & 31)) - 1u));
+  if (wi) {
+    const uint4* sec = reinterpret_cast<const uint4*>(W.bitmap) + 2 * (size_t)g1;
+    const uint4 a = __ldg(sec);
+    rank += __popc(a.x) + (wi > 1 ? __popc(a.y) : 0) + (wi > 2 ? __popc(a.z) : 0) + (wi > 3 ? __popc(a.w) : 0);
+    if (wi > 4) {
+      const uint4 b = __ldg(sec + 1);
+      rank += __popc(b.x) + (wi > 5 ? __popc(b.y) : 0) + (wi > 6 ? __popc(b.z) : 0);
+    }
+  }
+  return rank;
+}
+
 // Same contract as rule_lookup_kernel, for an INPUT level whose rows are in ascending flat order and
-// indexed by the bitmap/prefix workspace of the strided conv that produced it (no hash probes: one bitmap
-// word per candidate, and only for present neighbours one prefix pair + <= 1 sector of popcounts).
+// indexed by the bitmap/prefix workspace of the strided conv that produced it (no hash probes).
+// The kernel offsets of one (kz, ky) LINE address x-consecutive cells, i.e. consecutive bitmap bits, and rows are
+// numbered in flat order, so their ranks are consecutive too: one bitmap word (two when the run straddles a word)
+// answers "which of the line's neighbours exist", and only if one does, ONE prefix lookup ranks all of them
+// (rank of the next cell = rank + bit of this one) -- 9 line lookups per output row instead of 27 cell lookups
+// (5 instead of 13 for the mirrored SubM walk).
 __global__ void __launch_bounds__(256) rule_lookup_rank_kernel(ConvWs Win, const int4* __restrict__ out_idx,
                                                                const int* __restrict__ n_out, int out_cap,
                                                                ConvGeom G, int identity_kk, int mirror_kv,
                                                                int* __restrict__ nbr, int nbr_stride) {
   const int n = min(*n_out, out_cap);
-  // one thread per output row walks all kernel offsets: the row's coordinates are loaded once, neighbours
-  // along x share bitmap words (L1 hits), and for a fixed offset consecutive threads still write
-  // consecutive nbr entries
+  const int KX = G.ks[2];
   for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n; o += gridDim.x * blockDim.x) {
     const int4 c = out_idx[o];
-    int kk = 0;
+    const int x0 = c.w * G.stride[2] - G.pad[2];
+    int kk0 = 0;
     for (int kz = 0; kz < G.ks[0]; kz++) {
       const int z = c.y * G.stride[0] - G.pad[0] + kz * G.dil[0];
-      for (int ky = 0; ky < G.ks[1]; ky++) {
+      for (int ky = 0; ky < G.ks[1]; ky++, kk0 += KX) {
+        if (mirror_kv && kk0 > identity_kk) continue;  // whole line written by the mirrors of earlier offsets
         const int y = c.z * G.stride[1] - G.pad[1] + ky * G.dil[1];
         const bool zy_ok = z >= 0 && z < G.in_shape[0] && y >= 0 && y < G.in_shape[1];
-        const size_t row_base = (((size_t)c.x * G.in_shape[0] + z) * G.in_shape[1] + y) * G.in_shape[2];
-        for (int kx = 0; kx < G.ks[2]; kx++, kk++) {
-          int r;
-          if (mirror_kv && kk > identity_kk) continue;  // written by the mirror of an offset below the centre
+        const unsigned int row_base =
+            (unsigned int)((((size_t)c.x * G.in_shape[0] + z) * G.in_shape[1] + y) * G.in_shape[2]);
+        // pass 1: presence bits of the line's cells; pass 2 (only if any): ranks
+        unsigned int bits = 0u, w_cur = 0u, wq_cur = 0xFFFFFFFFu, first_word = 0u;
+        int first = -1;
+        for (int kx = 0; kx < KX; kx++) {
+          const int x = x0 + kx * G.dil[2];
+          if (!zy_ok || x < 0 || x >= G.in_shape[2]) continue;
+          const unsigned int cell = row_base + (unsigned int)x, wq = cell >> 5;
+          if (wq != wq_cur) {
+            w_cur = __ldg(&Win.bitmap[wq]);
+            wq_cur = wq;
+          }
+          if (w_cur & (1u << (cell & 31))) {
+            bits |= 1u << kx;
+            if (first < 0) {
+              first = kx;
+              first_word = w_cur;
+            }
+          }
+        }
+        int rank = 0;
+        if (first >= 0) rank = rank_before(Win, row_base + (unsigned int)(x0 + first * G.dil[2]), first_word);
+        for (int kx = 0; kx < KX; kx++) {
+          const int kk = kk0 + kx;
+          if (mirror_kv && kk > identity_kk) break;
+          int r = -1;
           if (kk == identity_kk) {
             r = o;
-          } else {
-            const int x = c.w * G.stride[2] - G.pad[2] + kx * G.dil[2];
-            r = (zy_ok && x >= 0 && x < G.in_shape[2]) ? rank_of_cell(Win, (unsigned int)(row_base + x)) : -1;
+          } else if (bits & (1u << kx)) {
+            // cells between two present neighbours of a line are x-consecutive only for dilation 1; with a dilated
+            // kernel the cells skipped in between may be active, so every present cell is ranked on its own
+            if (G.dil[2] == 1 || kx == first) {
+              r = rank;
+            } else {
+              const unsigned int cell = row_base + (unsigned int)(x0 + kx * G.dil[2]);
+              r = rank_before(Win, cell, __ldg(&Win.bitmap[cell >> 5]));
+            }
+            if (r >= Win.cap) r = -1;  // overflow rows do not exist (see rank_of_cell)
             if (mirror_kv && r >= 0) nbr[(size_t)(mirror_kv - 1 - kk) * nbr_stride + r] = o;
           }
+          if (bits & (1u << kx)) rank++;
           nbr[(size_t)kk * nbr_stride + o] = r;
         }
       }

@@ -13,14 +13,14 @@
 // 16-byte cp.async straight into the 128B-swizzled K-major A tiles the MMAs read from shared memory.
 // No conversion pass, no register staging, no TMEM operand.
 //
-// One persistent CTA per SM, warp specialised (672 threads):
+// One persistent CTA per SM, warp specialised (416 threads):
 //   warps 0-3  epilogue   : tcgen05.ld the 128 x COUT fp32 accumulator halves (lane = output row), add
 //                           them, apply scale/shift/ReLU, store the row as fp32 and/or packed bf16x2
 //   warp  4    MMA issuer : warp-uniform loop, one elected lane issues per pipeline slot (K = 64) 2*4
 //                           tcgen05.mma, M=128, K=16, both operands from shared memory:
 //                           A_h1 * [G1 | G2] (N = 2*COUT) and A_h2 * G1 (N = COUT); tcgen05.commit frees
 //                           the stage and publishes the accumulator through mbarriers
-//   warps 5-20 fetchers   : stage the tile's rule rows in shared memory (the next tile's are prefetched
+//   warps 5-12 fetchers   : stage the tile's rule rows in shared memory (the next tile's are prefetched
 //                           into registers), find the kernel offsets the tile uses, and for every slot
 //                           gather the neighbour rows (zero-fill for missing neighbours) with cp.async into
 //                           the stage's A tiles while one thread streams the slot's weight image with a
@@ -88,9 +88,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 // 16-byte asynchronous copy global -> shared; src_bytes = 0 writes zeros (missing neighbour)
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async16_cg(uint32_t dst, const void* src, uint32_t src_bytes) {  // L1 bypass
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 // the mbarrier receives one arrival once all cp.async issued so far by this thread have landed
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
@@ -199,7 +196,7 @@ __global__ void __launch_bounds__(32 * (kWarpFetch0 + kFetchWarps), 1)
 sparse_conv_tc_kernel(const unsigned char* __restrict__ feat, const unsigned char* __restrict__ wprep,
                       const int* __restrict__ nbr, int nbr_stride, const int* __restrict__ n_out_ptr, int out_cap,
                       int KV, const float* __restrict__ scale, const float* __restrict__ shift, int relu,
-                      float* __restrict__ out, unsigned char* __restrict__ out_packed, int bypass_l1) {
+                      float* __restrict__ out, unsigned char* __restrict__ out_packed) {
   using C = TcCfg<CIN, COUT>;
   extern __shared__ unsigned char smem_raw[];
   // round up to 1024 B (SWIZZLE_128B atoms) by OFFSETTING the __shared__ array: casting through an integer
@@ -348,18 +345,30 @@ sparse_conv_tc_kernel(const unsigned char* __restrict__ feat, const unsigned cha
     }
   } else {
     // =========================== fetchers ===========================
+    // What bounds this loop was measured on B200 by switching its parts off one at a time and by trying five
+    // alternative fetch schemes (profiles/r02_conv_fetch_bisect.md): with no MMAs, no gather copies and no weight
+    // stream the control skeleton alone still runs at ~700 clk per K=64 slot (full kernel ~900, the MMAs 444);
+    // every instruction added to the per-slot path of a fetch warp shows up 1:1 at ~5 clk (two fetch warps per
+    // scheduler: nothing hides a dependent chain) and every LDGSTS warp instruction costs ~8 clk of LSU time.
+    // Bytes, wavefronts, L2 and the tensor pipe are all far from their limits, so skipping absent rows
+    // (predicated, compacted with lane-masked MMAs, per-stage or alternating warp groups) lost more in added
+    // instructions than it saved. The loop is therefore kept as short as it gets: a lane's 8 rows are CONSECUTIVE,
+    // their rule entries arrive as two 128-bit shared loads, there is one LDGSTS form (no cache-policy twin), no
+    // per-row control flow, and every tile row is copied or zero-filled.
     constexpr int NF = kFetchWarps * 32;
+    static_assert(kFetchWarps == 8, "16 tile rows per fetch warp");
     constexpr int kRowBytes = 4 * CIN;  // packed source row: [h1 (2*CIN bytes) | h2 (2*CIN bytes)]
     const int fw = warp - kWarpFetch0, gt = fw * 32 + lane;
-    // copy geometry: 16 consecutive lanes cover one tile row (8 units of h1, 8 units of h2), two rows per
-    // warp instruction; unit u holds K-elements [8u, 8u+8) of the slot = channels c0.. of offset `off`
+    // copy geometry: 16 consecutive lanes cover one tile row (8 units of h1, 8 units of h2), two rows per warp
+    // instruction; unit u holds K-elements [8u, 8u+8) of the slot = channels ch0.. of stacked offset `off`
     const int rsub = lane >> 4, part = (lane >> 3) & 1, unit = lane & 7;
     const int off = (unit * 8) / CIN;
     const int src_byte = part * (2 * CIN) + ((unit * 8) % CIN) * 2;
-    constexpr int kRowStep = 2 * kFetchWarps, kRowsPerLane = kTileM / kRowStep;
-    const int row0 = fw * 2 + rsub;  // this lane copies rows row0 + kRowStep i; (row & 7) == (row0 & 7)
-    const uint32_t dst_lane =
-        smem_u32(ring) + (uint32_t)(part * kATileBytes + row0 * 128 + ((unit ^ (row0 & 7)) << 4));
+    constexpr int kRowsPerLane = 8;
+    const int row0 = 16 * fw + 8 * rsub;  // this lane copies rows row0 .. row0 + 7 (row0 % 8 == 0)
+    const uint32_t ring_u32 = smem_u32(ring);
+    const uint32_t dst_lane = ring_u32 + (uint32_t)(part * kATileBytes + row0 * 128);
+    const unsigned char* feat_lane = feat + src_byte;
 
     // rule rows of the NEXT tile, in flight while the current tile is fetched: thread -> row gt % 128, offsets
     // kpart + kParts j (kpart = gt / 128 is warp-uniform)
@@ -404,22 +413,18 @@ sparse_conv_tc_kernel(const unsigned char* __restrict__ feat, const unsigned cha
           meta[s].last = (mask == 0);
           meta[s].end = 0;
           mbar_arrive_expect_tx(&full[s], (uint32_t)C::kBBytes);
-          bulk_g2s(smem_u32(ring) + st + kABytes, wprep + (size_t)g * C::kBBytes, (uint32_t)C::kBBytes, &full[s]);
+          bulk_g2s(ring_u32 + st + kABytes, wprep + (size_t)g * C::kBBytes, (uint32_t)C::kBBytes, &full[s]);
         }
         const int kk = g * C::kGK + off;
         const bool kv_ok = kk < KV;  // the last group of a layer may be padded with non-existent offsets
-        const int* idx_row = idx_tile + (kv_ok ? kk : 0) * kTileM + row0;
-        int src[kRowsPerLane];
+        const int4* idx_row = reinterpret_cast<const int4*>(idx_tile + (kv_ok ? kk : 0) * kTileM + row0);
+        const int4 sa = idx_row[0], sb = idx_row[1];
+        const int src[kRowsPerLane] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
 #pragma unroll
-        for (int i = 0; i < kRowsPerLane; i++) src[i] = idx_row[kRowStep * i];
-#pragma unroll
-        for (int i = 0; i < kRowsPerLane; i++) {
+        for (int i = 0; i < kRowsPerLane; i++) {  // (row0 + i) & 7 == i: the swizzle phase is a compile-time constant
           const bool ok = kv_ok && src[i] >= 0;
-          const unsigned char* p = feat + (size_t)(ok ? src[i] : 0) * kRowBytes + src_byte;
-          if (bypass_l1)
-            cp_async16_cg(dst_lane + st + (uint32_t)(i * kRowStep * 128), p, ok ? 16u : 0u);
-          else
-            cp_async16(dst_lane + st + (uint32_t)(i * kRowStep * 128), p, ok ? 16u : 0u);
+          const unsigned char* p = feat_lane + (size_t)(ok ? src[i] : 0) * kRowBytes;
+          cp_async16(dst_lane + st + (uint32_t)(i * 128 + ((unit ^ i) << 4)), p, ok ? 16u : 0u);
         }
         cp_async_arrive_noinc(&full[s]);  // arrives when this thread's copies have landed
         q++;
@@ -501,27 +506,15 @@ int launch_tc(const unsigned char* feat, const unsigned char* wprep, const int* 
               unsigned char* out_packed, cudaStream_t st) {
   using C = TcCfg<CIN, COUT>;
   static PerDeviceOnce attr_once;
-  static int fetch_warps = 8, bypass_l1 = 0;
   if (attr_once.needed()) {
-    V3D_CUDA_TRY(cudaFuncSetAttribute(sparse_conv_tc_kernel<CIN, COUT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)C::kSmemBytes));
     V3D_CUDA_TRY(cudaFuncSetAttribute(sparse_conv_tc_kernel<CIN, COUT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)C::kSmemBytes));
-    V3D_CUDA_TRY(cudaFuncSetAttribute(sparse_conv_tc_kernel<CIN, COUT, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)C::kSmemBytes));
-    if (const char* e = getenv("V3D_TC_FETCH_WARPS")) fetch_warps = atoi(e);  // tuning knobs: 4, 8 or 16
-    if (const char* e = getenv("V3D_TC_BYPASS_L1")) bypass_l1 = atoi(e);
     attr_once.done();
   }
   const int tiles_cap = ceil_div(out_cap, kTileM);
   const int grid = tiles_cap < kNumSMs ? (tiles_cap > 0 ? tiles_cap : 1) : kNumSMs;
-#define V3D_TC_LAUNCH(FW)                                                                                          \
-  sparse_conv_tc_kernel<CIN, COUT, FW><<<grid, 32 * (kWarpFetch0 + FW), C::kSmemBytes, st>>>(                      \
-      feat, wprep, nbr, nbr_stride, n_out, out_cap, KV, scale, shift, relu, out, out_packed, bypass_l1)
-  if (fetch_warps == 4) V3D_TC_LAUNCH(4);
-  else if (fetch_warps == 16) V3D_TC_LAUNCH(16);
-  else V3D_TC_LAUNCH(8);
-#undef V3D_TC_LAUNCH
+  sparse_conv_tc_kernel<CIN, COUT, 8><<<grid, 32 * (kWarpFetch0 + 8), C::kSmemBytes, st>>>(
+      feat, wprep, nbr, nbr_stride, n_out, out_cap, KV, scale, shift, relu, out, out_packed);
   return check_launch();
 }
 

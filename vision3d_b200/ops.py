@@ -110,6 +110,32 @@ def nms_rotated(dets, scores, iou_threshold):
     return keep[: int(count.item())]
 
 
+def match_anchors(gt_bev, anchors_bev, thresholds, labels, want_vals=False):
+    """Fused box_iou_rotated + Matcher.__call__ (core/proposal_targets.py:53-60, ops/matcher.py:86-107).
+    gt_bev (M, 5), anchors_bev (N, 5) -> matches (N,) int64, labels (N,) int8 [, matched IoU (N,) f32].
+    `thresholds` / `labels` as given to the reference Matcher (thresholds WITHOUT the +-inf sentinels)."""
+    g = _cuda_f32(gt_bev, "gt_bev", 5)
+    a = _cuda_f32(anchors_bev, "anchors_bev", 5)
+    m, n = g.shape[0], a.shape[0]
+    th = [-float("inf")] + [float(t) for t in thresholds] + [float("inf")]
+    assert len(labels) == len(th) - 1
+    matches = torch.zeros(n, dtype=torch.int64, device=a.device)
+    if m == 0:  # matcher.py:73-84: no gt -> match 0, label of the lowest stratum
+        return (matches, torch.full((n,), int(labels[0]), dtype=torch.int8, device=a.device)) + (
+            (torch.zeros(n, dtype=_F32, device=a.device),) if want_vals else ())
+    lab = torch.empty(n, dtype=torch.int8, device=a.device)
+    vals = torch.empty(n, dtype=_F32, device=a.device) if want_vals else None
+    k = len(labels)
+    lo = (ctypes.c_float * k)(*th[:-1])
+    hi = (ctypes.c_float * k)(*th[1:])
+    lb = (ctypes.c_int * k)(*[int(v) for v in labels])
+    with torch.cuda.device(a.device):
+        check(_lib.load().v3d_match_anchors(g.data_ptr(), m, a.data_ptr(), n, k, lo, hi, lb, matches.data_ptr(),
+                                            lab.data_ptr(), vals.data_ptr() if vals is not None else None, _stream()),
+              "v3d_match_anchors")
+    return (matches, lab, vals) if want_vals else (matches, lab)
+
+
 # =============================================================================================
 # a1 / a2: voxelize
 # =============================================================================================

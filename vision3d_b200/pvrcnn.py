@@ -158,6 +158,9 @@ def init_for_benchmark(model, seed=0):
     g = torch.Generator().manual_seed(seed + 17)
     with torch.no_grad():
         for m in list(model.pnets.modules()) + list(model.roi_grid_pool.pnet.modules()):
+            if isinstance(m, nn.Conv2d):   # the modules' own kaiming draw comes from the global RNG: redraw it here so
+                fan = m.in_channels       # that two models built with the same seed are identical
+                m.weight.copy_(torch.randn(m.weight.shape, generator=g) * math.sqrt(2.0 / fan))
             if isinstance(m, nn.BatchNorm2d):
                 m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
                 m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) + 0.5)

@@ -31,12 +31,15 @@ from .compat import spconv
 # ---------------------------------------------------------------------------------------------------
 # configuration (reference core/config.py + configs/second/car.yaml)
 # ---------------------------------------------------------------------------------------------------
-_CAR = dict(names=["Car", "Van"], wlh=[1.6, 3.9, 1.56], yaw=[0.0, 1.501], score_thresh=0.3, center_z=-1.0)
+_CAR = dict(names=["Car", "Van"], wlh=[1.6, 3.9, 1.56], yaw=[0.0, 1.501], iou_thresh=[0.45, 0.60], score_thresh=0.3,
+            center_z=-1.0)
 _DEFAULT3 = [
-    dict(names=["Car", "Van"], wlh=[1.6, 3.9, 1.56], yaw=[0.0, math.pi / 2], score_thresh=0.3, center_z=-1.0),
-    dict(names=["Pedestrian", "Person_sitting"], wlh=[0.6, 0.8, 1.73], yaw=[0.0, math.pi / 2], score_thresh=0.3,
+    dict(names=["Car", "Van"], wlh=[1.6, 3.9, 1.56], yaw=[0.0, math.pi / 2], iou_thresh=[0.45, 0.60], score_thresh=0.3,
+         center_z=-1.0),
+    dict(names=["Pedestrian", "Person_sitting"], wlh=[0.6, 0.8, 1.73], yaw=[0.0, math.pi / 2], iou_thresh=[0.20, 0.35],
+         score_thresh=0.3, center_z=-0.6),
+    dict(names=["Cyclist"], wlh=[0.6, 1.76, 1.73], yaw=[0.0, math.pi / 2], iou_thresh=[0.20, 0.35], score_thresh=0.3,
          center_z=-0.6),
-    dict(names=["Cyclist"], wlh=[0.6, 1.76, 1.73], yaw=[0.0, math.pi / 2], score_thresh=0.3, center_z=-0.6),
 ]
 
 
