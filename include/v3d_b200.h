@@ -278,6 +278,29 @@ V3D_API int v3d_query_and_group_rows(const float* xyz, int xyz_stride, const flo
                                      const int* row_offsets, const float* new_xyz, const int* idx, int B, int M,
                                      int nsample, float* out, v3d_stream_t stream);
 
+/* SURVEY 8f-2 -- fused set abstraction: grouping (a10) -> shared MLP (two 1x1 convolutions, BatchNorm folded, ReLU) ->
+ * max over nsample, for one scale of a PointnetSAModuleMSG (detector/model.py:58-66, detector/roi_grid_pool.py:26-33,68),
+ * on the tensor cores (bf16 3-term split, fp32 accumulate, <= 1e-4 of the output scale); the grouped tensor
+ * (B, 3+C, M, nsample) and the MLP activations never reach HBM.
+ *   feat_packed : source rows [h1(0..Cp-1) | h2(0..Cp-1)] bf16, Cp = feature channels rounded up to 8 (zero padded);
+ *                 dense (row = b*N + idx) or ragged (row = row_offsets[b] + idx, DEVICE int[B+1]) like v3d_ball_query_msg
+ *   xyz / new_xyz / idx : as v3d_query_and_group_rows; nsample must be 16 or 32
+ *   w1_prepared : v3d_sa_mlp_prepare of the layer-1 weights as (ceil((Cp+3)/64), 64, N1) fp32 chunks in K order
+ *                 [features 0..Cp-1 | dx dy dz | 0...] (the reference's input order is [xyz ; features]: permute rows)
+ *   w2_prepared : v3d_sa_mlp_prepare of the layer-2 weights as (ceil(N1/64), 64, N2) chunks; b1[N1], b2[N2] folded biases
+ *   out[B, c_total, M] receives channels [c_off, c_off + N2). (N1, N2) in {(16,16), (32,32), (64,64), (192,96)}. */
+V3D_API size_t v3d_sa_mlp_prepared_bytes(int n_chunks, int N);
+V3D_API int v3d_sa_mlp_prepare(const float* weight_chunks, int n_chunks, int N, void* prepared, size_t prepared_bytes,
+                               v3d_stream_t stream);
+V3D_API int v3d_sa_fused(const void* feat_packed, int Cp, const float* xyz, int xyz_stride, const int* row_offsets, int N,
+                         const float* new_xyz, const int* idx, int B, int M, int nsample, const void* w1_prepared,
+                         const float* b1, int N1, const void* w2_prepared, const float* b2, int N2, float* out,
+                         int c_total, int c_off, v3d_stream_t stream);
+/* fp32 feat[b, c, n] (element strides given) -> packed rows (B*N, 2*Cp) bf16 [h1 | h2], channels C..Cp-1 zero: the
+ * gather source format of v3d_sa_fused for channel-major tensors (keypoint features (B, 512, 2048), point intensity) */
+V3D_API int v3d_pack_channel_major(const float* feat, long long b_stride, long long c_stride, long long n_stride, int B,
+                                   int C, int N, int Cp, void* packed, v3d_stream_t stream);
+
 /* a15 on the device: offsets[b] = first row of frame b in a (b,z,y,x)-ordered index list, offsets[B] = n_rows
  * (= torchsearchsorted.searchsorted(batch_index, arange(B+1)), compute_pad_amounts, detector/sparse_cnn.py:107-116,
  * without its .cpu().numpy() round trip). */

@@ -21,14 +21,16 @@ def _inputs(B, n, seed=0, npts=16384):
     return clouds, props, grid
 
 
-@pytest.mark.parametrize("B,n", [(2, 16), (8, 100)])
-def test_keypoint_stage_vs_cpu_composition(cuda, B, n):
+@pytest.mark.parametrize("B,n,fused", [(2, 16, True), (2, 16, False), (8, 100, True)])
+def test_keypoint_stage_vs_cpu_composition(cuda, B, n, fused):
     """(8, 100) is config C3 at full size: FPS-2048 on 8 clouds of 16 384 points, 5-source VSA, RoI-grid pool
     with 100 proposals x 16 grid points per frame."""
     cfg = pvrcnn.PVRCNNConfig()
     model = pvrcnn.init_for_benchmark(pvrcnn.PVRCNNB200(cfg), 0)
     clouds, props, grid = _inputs(B, n)
-    stage = pvrcnn.KeypointStage(model, B, 16384, n, cuda)
+    # fused=True: grouping -> shared MLP -> max in ONE tensor-core kernel per scale (SURVEY 8f-2, v3d_sa_fused);
+    # fused=False: a10 grouping kernels + the MLP / max in torch (the reference-shaped composition)
+    stage = pvrcnn.KeypointStage(model, B, 16384, n, cuda, fused_sa=fused)
     stage.load(clouds, grid)
     pooled = stage.step()
     torch.cuda.synchronize()
@@ -68,7 +70,7 @@ def test_keypoint_stage_vs_cpu_composition(cuda, B, n):
     for r in range(2):
         assert np.array_equal(stage.roi_idx[r].cpu().numpy(), np.stack(st["roi_idx"][r], 0)), r
     err = float((pooled.cpu() - want).abs().max() / want.abs().max())
-    print("C3 B=%d n=%d: pooled err %.2e" % (B, n, err))
+    print("C3 B=%d n=%d fused_sa=%s: pooled err %.2e" % (B, n, fused, err))
     assert pooled.shape == (B, n, 256) and err <= 1e-4, err
 
 
@@ -80,7 +82,7 @@ def test_reference_shaped_methods_match_stage(cuda):
     cfg = pvrcnn.PVRCNNConfig()
     model = pvrcnn.init_for_benchmark(pvrcnn.PVRCNNB200(cfg), 0)
     clouds, props, grid = _inputs(B, n, seed=3)
-    stage = pvrcnn.KeypointStage(model, B, 16384, n, cuda)
+    stage = pvrcnn.KeypointStage(model, B, 16384, n, cuda, fused_sa=False)
     stage.load(clouds, grid)
     stage.step()
     pts = stage.points
@@ -211,3 +213,37 @@ def test_fused_anchor_matching_vs_expression_path_and_reference_golden(cuda):
         common = np.intersect1d(pos, gold[tag + "_pos"], return_indices=True)
         reg = i1["G_reg"].reshape(-1, 7)[torch.from_numpy(common[0]).to(cuda)].cpu().numpy()
         np.testing.assert_allclose(reg, gold[tag + "_reg_pos"][common[2]], rtol=0, atol=1e-5)
+
+
+@pytest.mark.parametrize("C,widths,ns", [(1, (8, 16), 16), (4, (8, 16), 32), (32, (32, 32), 16), (64, (64, 64), 32),
+                                         (512, (192, 96), 16)])
+def test_sa_fused_kernel_vs_torch_expression(cuda, C, widths, ns):
+    """v3d_sa_fused (one scale: grouping -> 1x1 conv + ReLU -> 1x1 conv + ReLU -> max) vs QueryAndGroup + torch
+    fp32 convolutions on the same ball-query indices; ragged sources; <= 1e-4 of the output scale."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(C)
+    B, M = 2, 300                                     # 600 queries -> partial last tile for ns = 16 (9600 rows = 75 tiles)
+    lens = [900, 1500]
+    offs = torch.tensor([0, 900, 2400], dtype=torch.int32, device=cuda)
+    xyz = (torch.rand((2400, 3), generator=g) * 4).to(cuda)
+    feat = torch.randn((2400, C), generator=g).to(cuda)
+    q = (torch.rand((B, M, 3), generator=g) * 4).to(cuda)
+    idx = ops.ball_query_msg([0.7], [ns], xyz, q, offs)[0]
+    n1, n2 = widths
+    w1 = (torch.randn((n1, 3 + C), generator=g) / (3 + C) ** 0.5).to(cuda)
+    b1 = (torch.randn(n1, generator=g) * 0.1).to(cuda)
+    w2 = (torch.randn((n2, n1), generator=g) / n1 ** 0.5).to(cuda)
+    b2 = (torch.randn(n2, generator=g) * 0.1).to(cuda)
+    grouped = ops.query_and_group_rows(xyz, feat, q, idx, offs)                       # (B, 3 + C, M, ns)
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        h = F.relu(F.conv2d(grouped, w1[:, :, None, None], b1))
+        want = F.relu(F.conv2d(h, w2[:, :, None, None], b2)).amax(3)                  # (B, n2, M)
+    Cp = -(-C // 8) * 8
+    packed = ops.pack_channel_major(feat.t().unsqueeze(0), Cp)                        # (1, C, rows) view -> (rows, 2 Cp)
+    mlp = ops.PreparedSaMlp([(w1, b1), (w2, b2)], C)
+    out = torch.full((B, n2 + 5, M), -7.0, device=cuda)
+    ops.sa_fused(packed, xyz, q, idx, mlp, out, c_off=3, row_offsets=offs)
+    torch.cuda.synchronize()
+    err = float((out[:, 3:3 + n2] - want).abs().max() / want.abs().max())
+    assert err <= 1e-4, err
+    assert bool((out[:, :3] == -7.0).all()) and bool((out[:, 3 + n2:] == -7.0).all())   # only its channel slice is written

@@ -63,6 +63,12 @@ SIGNATURES = {
     "v3d_fps_keypoints": (c_int, [P, c_int, c_int, c_int, c_int, P, P, P]),
     "v3d_ball_query_msg": (c_int, [P, c_int, P, P, c_int, c_int, c_int, c_int, P, P, P, P]),
     "v3d_query_and_group_rows": (c_int, [P, c_int, P, c_int, c_int, c_int, P, P, P, c_int, c_int, c_int, P, P]),
+    "v3d_sa_mlp_prepared_bytes": (c_size_t, [c_int, c_int]),
+    "v3d_sa_mlp_prepare": (c_int, [P, c_int, c_int, P, c_size_t, P]),
+    "v3d_sa_fused": (c_int, [P, c_int, P, c_int, P, c_int, P, P, c_int, c_int, c_int, P, P, c_int, P, P, c_int, P,
+                             c_int, c_int, P]),
+    "v3d_pack_channel_major": (c_int, [P, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, c_int, c_int, c_int,
+                                       c_int, P, P]),
     "v3d_batch_offsets": (c_int, [P, P, c_int, c_int, P, P]),
     "v3d_to_global": (c_int, [P, P, c_int, P, P, P, P]),
     "v3d_pad_batch": (c_int, [P, c_int, P, c_int, c_int, ctypes.c_ulonglong, P, P]),

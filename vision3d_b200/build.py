@@ -30,6 +30,7 @@ UNITS = {
     "dense.cu": [],
     "head.cu": ["-fmad=false"],
     "pointops.cu": [],
+    "sa_fused.cu": [],
 }
 
 

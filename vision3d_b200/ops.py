@@ -591,6 +591,86 @@ def pad_batch(src, row_offsets, batch_size, frame_capacity, seed=0, out=None):
 
 
 # =============================================================================================
+# 8f-2: fused set abstraction (grouping -> shared MLP -> max) on the tensor cores
+# =============================================================================================
+_SA_SHAPES = {(16, 16), (32, 32), (64, 64), (192, 96)}
+
+
+class PreparedSaMlp:
+    """Weights of ONE scale of a PointnetSAModuleMSG (two 1x1 conv layers, BatchNorm already folded:
+    [(W1 (n1, 3 + C), b1 (n1,)), (W2 (n2, n1), b2 (n2,))], input channel order [xyz ; features] as QueryAndGroup
+    emits it) in the layout v3d_sa_fused consumes: K order [features | pad to Cp | xyz | 0], widths padded to the
+    supported (N1, N2), bf16 3-term split, swizzled chunk images."""
+
+    def __init__(self, layers, C, Cp=None):
+        (w1, b1), (w2, b2) = layers
+        dev = w1.device
+        n1, n2 = w1.shape[0], w2.shape[0]
+        assert w1.shape[1] == 3 + C and w2.shape[1] == n1
+        self.C, self.Cp = int(C), int(Cp) if Cp else -(-int(C) // 8) * 8   # Cp: channels of the packed source rows
+        assert self.Cp >= C and self.Cp % 8 == 0
+        self.N1 = max(16, -(-n1 // 16) * 16)
+        self.N2 = n2
+        if (self.N1, self.N2) not in _SA_SHAPES:
+            raise V3DError("unsupported shared-MLP widths %s" % ((n1, n2),))
+        self.nc1, self.nc2 = -(-(self.Cp + 3) // 64), -(-self.N1 // 64)
+        k1 = torch.zeros((self.nc1 * 64, self.N1), dtype=_F32, device=dev)
+        k1[:C, :n1] = w1[:, 3:].t()
+        k1[self.Cp:self.Cp + 3, :n1] = w1[:, :3].t()
+        k2 = torch.zeros((self.nc2 * 64, self.N2), dtype=_F32, device=dev)
+        k2[:n1] = w2.t()
+        self.b1 = torch.zeros(self.N1, dtype=_F32, device=dev)
+        self.b1[:n1] = b1
+        self.b2 = b2.detach().float().contiguous()
+        lib = _lib.load()
+        self.w1 = torch.empty(lib.v3d_sa_mlp_prepared_bytes(self.nc1, self.N1), dtype=torch.uint8, device=dev)
+        self.w2 = torch.empty(lib.v3d_sa_mlp_prepared_bytes(self.nc2, self.N2), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.v3d_sa_mlp_prepare(k1.contiguous().data_ptr(), self.nc1, self.N1, self.w1.data_ptr(), self.w1.numel(),
+                                         _stream()), "v3d_sa_mlp_prepare")
+            check(lib.v3d_sa_mlp_prepare(k2.contiguous().data_ptr(), self.nc2, self.N2, self.w2.data_ptr(), self.w2.numel(),
+                                         _stream()), "v3d_sa_mlp_prepare")
+        torch.cuda.current_stream(dev).synchronize()  # k1 / k2 are temporaries
+
+
+def pack_channel_major(feat, Cp=None, out=None):
+    """fp32 feat (B, C, N) with arbitrary strides -> packed rows (B*N, 2*Cp) bf16 [h1 | h2] (Cp >= C, multiple of 8)."""
+    if not feat.is_cuda or feat.dtype != _F32 or feat.dim() != 3:
+        raise V3DError("feat must be a CUDA float32 (B, C, N) tensor")
+    B, C, N = feat.shape
+    Cp = int(Cp or -(-C // 8) * 8)
+    if out is None:
+        out = torch.empty((B * N, 2 * Cp), dtype=torch.bfloat16, device=feat.device)
+    assert out.shape == (B * N, 2 * Cp) and out.dtype == torch.bfloat16
+    sb, sc, sn = feat.stride()
+    with torch.cuda.device(feat.device):
+        check(_lib.load().v3d_pack_channel_major(feat.data_ptr(), sb, sc, sn, B, C, N, Cp, out.data_ptr(), _stream()),
+              "v3d_pack_channel_major")
+    return out
+
+
+def sa_fused(feat_packed, xyz, new_xyz, idx, mlp, out, c_off=0, row_offsets=None):
+    """One scale of a set-abstraction module, fused (v3d_sa_fused). feat_packed (rows, 2*Cp) bf16; xyz (B, N, S) or
+    (rows, S) f32 (S >= 3); new_xyz (B, M, 3); idx (B, M, ns) int32, ns in {16, 32}; mlp: PreparedSaMlp;
+    out (B, c_total, M) f32 receives channels [c_off, c_off + mlp.N2)."""
+    x = _cuda_f32(xyz, "xyz")
+    q = _cuda_f32(new_xyz, "new_xyz", 3)
+    i = _cuda_i32(idx, "idx")
+    B, M, ns = i.shape
+    S = x.shape[-1]
+    N = x.shape[1] if row_offsets is None else 0
+    assert feat_packed.dtype == torch.bfloat16 and feat_packed.shape[-1] == 2 * mlp.Cp and feat_packed.is_contiguous()
+    assert out.dtype == _F32 and out.is_contiguous() and out.shape[0] == B and out.shape[2] == M
+    with torch.cuda.device(x.device):
+        check(_lib.load().v3d_sa_fused(feat_packed.data_ptr(), mlp.Cp, x.data_ptr(), S,
+                                       row_offsets.data_ptr() if row_offsets is not None else None, N, q.data_ptr(),
+                                       i.data_ptr(), B, M, ns, mlp.w1.data_ptr(), mlp.b1.data_ptr(), mlp.N1,
+                                       mlp.w2.data_ptr(), mlp.b2.data_ptr(), mlp.N2, out.data_ptr(), out.shape[1],
+                                       int(c_off), _stream()), "v3d_sa_fused")
+    return out
+
+
+# =============================================================================================
 # SECOND head glue (engine-internal)
 # =============================================================================================
 def second_head_decode(reg_out, anchors, anchor_idx, n_cls, n_yaw, topk, boxes=None, nms_in=None):

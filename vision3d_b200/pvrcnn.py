@@ -213,7 +213,8 @@ class KeypointStage:
     step outputs: self.keypoints (B, 2048, 3), self.kp_idx (B, 2048) int32, self.kp_features (B, 512, 2048),
                   self.pooled (B, n, 256); per-source ball-query indices in self.sa_idx for the parity tests."""
 
-    def __init__(self, model: PVRCNNB200, batch_size, points_per_frame, n_proposals, device, level_caps=None):
+    def __init__(self, model: PVRCNNB200, batch_size, points_per_frame, n_proposals, device, level_caps=None,
+                 fused_sa=True):
         cfg = model.cfg
         self.cfg, self.B, self.N, self.n = cfg, int(batch_size), int(points_per_frame), int(n_proposals)
         self.dev = dev = torch.device(device)
@@ -243,6 +244,16 @@ class KeypointStage:
         Mg = self.n * cfg.GRIDPOOL_NUM_GRIDPOINTS
         self.roi_idx = [torch.zeros((B, Mg, ns), dtype=torch.int32, device=dev) for ns in cfg.SAMPLES_PN]
         self.kp_features = torch.zeros((B, 512, M), dtype=torch.float32, device=dev)
+        # fused set abstraction: grouping -> shared MLP -> max in one tensor-core kernel per scale
+        self.fused_sa = bool(fused_sa)
+        if self.fused_sa:
+            src_c = [1, 4, 32, 64, 64]
+            src_cp = [8, 16, 32, 64, 64]   # channels of the packed source rows (x0: the engine's 16-channel pack)
+            self.sa_prepared = [[ops.PreparedSaMlp(l, src_c[i], src_cp[i]) for l in self.sa_mlps[i]] for i in range(5)]
+            self.roi_prepared = [ops.PreparedSaMlp(l, 512) for l in self.roi_mlps]
+            self.pts_packed = torch.zeros((B * self.N, 16), dtype=torch.bfloat16, device=dev)
+            self.kp_packed = torch.zeros((B * M, 1024), dtype=torch.bfloat16, device=dev)
+            self.roi_feat = torch.zeros((B, 192, Mg), dtype=torch.float32, device=dev)
         self.pooled = None
         self.timings = {}
         self._build_plan()
@@ -281,6 +292,32 @@ class KeypointStage:
         c0 = self._sa_c0[i] + sum(m[-1][0].shape[0] for m in self.sa_mlps[i][:r])
         self.kp_features[:, c0:c0 + o.shape[1]] = o
 
+    def _packed_source(self, i):
+        e = self.eng
+        if i == 0:
+            return self.pts_packed
+        return e.featp[0][2] if i == 1 else e.featp[i - 1][0]
+
+    def _sa_fused(self, i, r):
+        xyz, _, offs = self._source(i)
+        ops.sa_fused(self._packed_source(i), xyz, self.keypoints, self.sa_idx[i][r], self.sa_prepared[i][r],
+                     self.kp_features, c_off=self._sa_c0[i] + sum(m.N2 for m in self.sa_prepared[i][:r]), row_offsets=offs)
+
+    def _pack_points(self):   # intensity column of the raw (B, N, 4) rows -> 8-channel packed rows
+        ops.pack_channel_major(self.points[..., 3].unsqueeze(1), 8, out=self.pts_packed)
+
+    def _roi_pack(self):
+        ops.pack_channel_major(self.kp_features, 512, out=self.kp_packed)
+
+    def _roi_fused(self, r):
+        ops.sa_fused(self.kp_packed, self.keypoints, self.gridpoints, self.roi_idx[r], self.roi_prepared[r],
+                     self.roi_feat, c_off=96 * r)
+
+    def _roi_reduce_fused(self):
+        B, n, m = self.B, self.n, self.cfg.GRIDPOOL_NUM_GRIDPOINTS
+        f = self.roi_feat.view(B, -1, n, m).permute(0, 2, 1, 3).contiguous().view(B, n, -1)   # roi_grid_pool.py:69-70
+        self.pooled = self.model.roi_grid_pool.reduction(f)
+
     def _roi_query(self):
         pn = self.model.roi_grid_pool.pnet
         ops.ball_query_msg([g.radius for g in pn.groupers], self.cfg.SAMPLES_PN, self.keypoints, self.gridpoints, None,
@@ -316,18 +353,29 @@ class KeypointStage:
         for name, _, fn in self.eng.plan[:self.eng.n_backbone_ops]:
             plan.append(("backbone/" + name, fn))
         plan.append(("offsets+to_global", self._levels))
+        if self.fused_sa:
+            plan.append(("pack_points", self._pack_points))
         for i in range(5):
             plan.append(("sa%d/ball_query" % i, (lambda i=i: self._sa_query(i))))
             for r in range(len(self.cfg.SAMPLES_PN)):
-                plan.append(("sa%d/group_r%d" % (i, r), (lambda i=i, r=r: self._sa_group(i, r))))
-                plan.append(("sa%d/mlp+max_r%d(torch)" % (i, r), (lambda i=i, r=r: self._sa_mlp(i, r))))
+                if self.fused_sa:
+                    plan.append(("sa%d/fused_group+mlp+max_r%d" % (i, r), (lambda i=i, r=r: self._sa_fused(i, r))))
+                else:
+                    plan.append(("sa%d/group_r%d" % (i, r), (lambda i=i, r=r: self._sa_group(i, r))))
+                    plan.append(("sa%d/mlp+max_r%d(torch)" % (i, r), (lambda i=i, r=r: self._sa_mlp(i, r))))
         plan.append(("bev_gather(torch)", self._bev))
         plan.append(("roi/ball_query", self._roi_query))
         self._roi_out = [None] * len(self.cfg.SAMPLES_PN)
-        for r in range(len(self.cfg.SAMPLES_PN)):
-            plan.append(("roi/group_r%d" % r, (lambda r=r: self._roi_group(r))))
-            plan.append(("roi/mlp+max_r%d(torch)" % r, (lambda r=r: self._roi_mlp(r))))
-        plan.append(("roi/reduction_mlp(torch)", self._roi_reduce))
+        if self.fused_sa:
+            plan.append(("roi/pack_keypoint_features", self._roi_pack))
+            for r in range(len(self.cfg.SAMPLES_PN)):
+                plan.append(("roi/fused_group+mlp+max_r%d" % r, (lambda r=r: self._roi_fused(r))))
+            plan.append(("roi/reduction_mlp(torch)", self._roi_reduce_fused))
+        else:
+            for r in range(len(self.cfg.SAMPLES_PN)):
+                plan.append(("roi/group_r%d" % r, (lambda r=r: self._roi_group(r))))
+                plan.append(("roi/mlp+max_r%d(torch)" % r, (lambda r=r: self._roi_mlp(r))))
+            plan.append(("roi/reduction_mlp(torch)", self._roi_reduce))
         self.plan = plan
 
     def load(self, clouds, gridpoints):

@@ -404,8 +404,11 @@ class SecondEngine:
         self.feat = [[torch.empty((self.caps[lv], cmax[lv]), dtype=torch.float32, device=dev) for _ in range(2)]
                      for lv in range(5)]
         # packed (bf16 h1|h2) twins for the tensor-core layers: two ping-pong buffers + one for packing fp32 input
+        # (keep_level_features: a third buffer per level so that the packed rows ENTERING a level survive its SubM
+        # layers -- they are the gather source of the fused set abstraction, pvrcnn.KeypointStage)
         self.featp = [[torch.empty((self.caps[lv], 2 * cmax[lv]), dtype=torch.bfloat16, device=dev)
-                       for _ in range(3 if lv == 0 else 2)] for lv in range(5)] if tensor_cores else None
+                       for _ in range(3 if (lv == 0 or keep_level_features) else 2)] for lv in range(5)] \
+            if tensor_cores else None
         self.dense_out = torch.empty((B, 64, *shapes[4]), dtype=torch.float32, device=dev)
         self.dense_ws = torch.empty(ops._lib.load().v3d_sparse_to_dense_workspace_bytes(B, ops.i3(shapes[4])),
                                     dtype=torch.uint8, device=dev)
@@ -511,7 +514,7 @@ class SecondEngine:
                 """One fused conv layer. Tensor-core layers consume and produce PACKED rows (the packed twin
                 of the fp32 buffer, same bytes); fp32 rows are only written where something reads them: the
                 exact-fp32 first layer and the last layer (-> dense BEV)."""
-                out32 = self.feat[lv_out][buf]
+                out32 = self.feat[lv_out][buf if buf < 2 else 1]  # (fp32 twin: only written by non-TC / last layers)
                 assert out32.shape[1] == d["cout"]
                 tc = isinstance(d["w"], ops.PreparedWeights) and d["w"].buf is not None
                 if not tc:
@@ -538,7 +541,8 @@ class SecondEngine:
                 d = self.layers[li]
                 x = conv_op("subm_L%d_%d_%dx%d" % (lv, k, d["cin"], d["cout"]), d, x, self.nbr_subm[lv],
                             self.n_rows[lv], self.caps[lv], lv, cur, False)
-                cur, li, k = cur ^ 1, li + 1, k + 1
+                cur = (3 - cur) if (self.keep_level_features and lv > 0 and self.featp is not None) else cur ^ 1
+                li, k = li + 1, k + 1
             d = self.layers[li]
             plan.append(("rulebook_conv_L%d" % lv, 5, (lambda d=d, lv=lv, index=index: ops.rulebook_conv(
                 index, self.indices[lv], self.n_rows[lv], B, self.shapes[lv], d["ks"], d["stride"],
