@@ -647,8 +647,13 @@ def run_b200(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        # every rank has issued its last collective; leave without ncclCommDestroy: tearing the communicator down
+        # while CUDA graphs that captured its all-gather are still alive blocked for minutes on the GPU box
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize(dev)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return line
 
 

@@ -658,9 +658,13 @@ class SecondEngine:
         current stream after a full step has populated the buffers. Returns [(name, us)]."""
         out = []
         with torch.no_grad():
-            self._step()
+            for name, _, fn in self.plan:   # one full local pass populates the buffers
+                if not name.startswith("allgather"):
+                    fn()
             torch.cuda.synchronize(self.dev)
             for name, _, fn in self.plan:
+                if name.startswith("allgather"):  # a collective: the other ranks are not profiling with us
+                    continue
                 fn()
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
