@@ -215,6 +215,18 @@ V3D_API int v3d_sparse_conv_fwd_tc(const void* feat_packed, const void* prepared
                                    const float* scale, const float* shift, int relu, float* out,
                                    void* out_packed, v3d_stream_t stream);
 
+/* SURVEY 8f-1 -- backward of the sparse convolution (SparseConvFunction / SubMConvFunction.backward of spconv v1.x, the
+ * autograd Functions behind the layers of detector/sparse_cnn.py:15-30; needed by train.py:57-72), exact fp32:
+ *   dX : v3d_sparse_conv_fwd(grad_out, W^T per offset (KV, Cout, Cin), inv, ...) on the inverted rule table
+ *        inv[k][i] = o  <=>  nbr[k][o] = i  (v3d_rulebook_invert; for SubM rule books inv[k] = nbr[KV-1-k], no build);
+ *   dW : v3d_sparse_conv_bwd_weight: grad_weight[k] = sum_o feat[nbr[k][o]]^T grad_out[o] (zeroed, then accumulated
+ *        with one atomicAdd per element and 1024-row chunk: fp32 summation order is not fixed). */
+V3D_API int v3d_rulebook_invert(const int* nbr, int nbr_stride, const int* n_out, int out_capacity, int kernel_volume,
+                                int* inv, int inv_stride, v3d_stream_t stream);
+V3D_API int v3d_sparse_conv_bwd_weight(const float* feat, const float* grad_out, const int* nbr, int nbr_stride,
+                                       const int* n_out, int out_capacity, int kernel_volume, int Cin, int Cout,
+                                       float* grad_weight, v3d_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * a3  SparseConvTensor.dense(): (N,C) rows -> (B,C,D,H,W), zero filled (sparse_cnn.py:128-133).
  * workspace holds the (B,D,H,W) int32 cell->row map.

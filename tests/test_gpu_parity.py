@@ -539,3 +539,58 @@ def test_grouped_nms_equals_global_nms_on_offset_groups(cuda):
         n0, n1 = int(c0.item()), int(c1.item())
         assert n0 == n1 and torch.equal(k0[:n0], k1[:n1])
         assert np.array_equal(k1[:n1].cpu().numpy(), oracle.nms_rotated(off, scores, 0.01, 1))
+
+
+# ------------------------------------------------------------------------------------ sparse conv backward (8f-1)
+@pytest.mark.parametrize("subm,cin,cout", [(True, 8, 16), (False, 16, 32), (True, 64, 64), (False, 4, 16)])
+def test_sparse_conv_backward_vs_dense_conv3d_autograd(cuda, subm, cin, cout):
+    """Hand-written backward (dX: forward kernel on the inverted rule table with W^T; dW: v3d_sparse_conv_bwd_weight)
+    through the compat spconv autograd Function, against torch autograd of a float64 dense conv3d on the densified
+    input, gradients read back at the active sites. <= 1e-4 of the gradient scale (fp32 kernels: ~1e-6)."""
+    import torch.nn.functional as F
+    from vision3d_b200.compat import spconv
+    shape, B = [7, 14, 12], 2
+    idx = synth.make_clustered_sites(5, 260, shape, B)
+    ii = torch.from_numpy(idx.astype(np.int64))
+    torch.manual_seed(1)
+    feats = torch.randn(len(idx), cin, device=cuda, requires_grad=True)
+    if subm:
+        conv = spconv.SubMConv3d(cin, cout, 3, indice_key="k", bias=False).to(cuda)
+        kw = dict(padding=1)
+    else:
+        conv = spconv.SparseConv3d(cin, cout, 3, 2, padding=[0, 1, 1], bias=False).to(cuda)
+        kw = dict(stride=2, padding=(0, 1, 1))
+    conv.train()
+    y = conv(spconv.SparseConvTensor(feats, torch.from_numpy(idx).to(cuda), shape, B))
+    R = torch.randn_like(y.features)
+    (y.features * R).sum().backward()
+    # float64 dense reference on the CPU
+    dense_in = torch.zeros((B, cin, *shape), dtype=torch.float64)
+    dense_in[ii[:, 0], :, ii[:, 1], ii[:, 2], ii[:, 3]] = feats.detach().double().cpu()
+    dense_in.requires_grad_(True)
+    w64 = conv.weight.detach().double().cpu().requires_grad_(True)           # (k0, k1, k2, Cin, Cout)
+    out = F.conv3d(dense_in, w64.permute(4, 3, 0, 1, 2), **kw)
+    oi = y.indices.long().cpu()
+    got_fwd = y.features.detach().double().cpu()
+    ref_fwd = out[oi[:, 0], :, oi[:, 1], oi[:, 2], oi[:, 3]]
+    assert float((got_fwd - ref_fwd).abs().max() / ref_fwd.abs().max()) <= 1e-5
+    (ref_fwd * R.double().cpu()).sum().backward()
+    g_in = dense_in.grad[ii[:, 0], :, ii[:, 1], ii[:, 2], ii[:, 3]]
+    err_x = float((feats.grad.double().cpu() - g_in).abs().max() / g_in.abs().max())
+    err_w = float((conv.weight.grad.double().cpu() - w64.grad).abs().max() / w64.grad.abs().max())
+    assert err_x <= 1e-4 and err_w <= 1e-4, (err_x, err_w)
+
+
+def test_rulebook_invert_is_the_inverse(cuda):
+    from vision3d_b200 import ops
+    shape, B = [9, 30, 28], 2
+    idx = synth.make_clustered_sites(2, 400, shape, B)
+    ind, n_rows, table, cap = _site_setup(cuda, idx, shape)
+    oi, want_nbr, _ = oracle.rulebook_conv(idx, shape, 3, 2, 1)
+    _, n_out, nbr, _ = ops.rulebook_conv(table, ind, n_rows, B, shape, 3, 2, 1, 1, len(oi) + 3)
+    inv = ops.rulebook_invert(nbr, n_out, len(oi) + 3, len(idx)).cpu().numpy()
+    want = np.full((27, len(idx)), -1, np.int32)
+    for k in range(27):
+        o = np.nonzero(want_nbr[k] >= 0)[0]
+        want[k, want_nbr[k, o]] = o
+    assert np.array_equal(inv, want)

@@ -40,6 +40,8 @@ SIGNATURES = {
     "v3d_rulebook_conv_ranked": (c_int, [P, c_int, P, P, c_int, c_int, P, P, P, P, P, P, P, c_int, P, c_int, P,
                                          c_size_t, P]),
     "v3d_sparse_conv_fwd": (c_int, [P, P, P, c_int, P, c_int, c_int, c_int, c_int, P, P, c_int, P, P]),
+    "v3d_rulebook_invert": (c_int, [P, c_int, P, c_int, c_int, P, c_int, P]),
+    "v3d_sparse_conv_bwd_weight": (c_int, [P, P, P, c_int, P, c_int, c_int, c_int, c_int, P, P]),
     "v3d_sparse_conv_prepared_bytes": (c_size_t, [c_int, c_int, c_int]),
     "v3d_sparse_conv_prepare": (c_int, [P, c_int, c_int, c_int, P, c_size_t, P]),
     "v3d_feature_pack": (c_int, [P, P, c_int, c_int, c_int, P, P]),

@@ -26,6 +26,7 @@ UNITS = {
     "voxelize.cu": [],
     "rulebook.cu": [],
     "sparse_conv.cu": [],
+    "sparse_conv_bwd.cu": [],
     "sparse_conv_tc.cu": [],
     "dense.cu": [],
     "head.cu": ["-fmad=false"],

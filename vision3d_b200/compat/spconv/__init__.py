@@ -136,35 +136,26 @@ class _SparseConvFunction(torch.autograd.Function):
     fused sm_100a kernel; backward (training side) is composed from torch index ops."""
 
     @staticmethod
-    def forward(ctx, features, weight, nbr, n_out_dev, n_out, scale, shift, relu):
+    def forward(ctx, features, weight, nbr, n_out_dev, n_out, scale, shift, relu, subm=False):
         prepared = isinstance(weight, ops.PreparedWeights)
         out = ops.sparse_conv(features.contiguous(), weight if prepared else weight.contiguous(), nbr, n_out_dev,
                               max(n_out, 1), scale, shift, relu)
         if not prepared:
             ctx.save_for_backward(features, weight, nbr)
-        ctx.n_out = n_out
+        ctx.n_out, ctx.n_out_dev, ctx.subm = n_out, n_out_dev, bool(subm)
         ctx.fused = scale is not None or relu or prepared
         return out[:n_out]
 
     @staticmethod
     def backward(ctx, grad_out):
+        """Hand-written kernels: dX = forward kernel on the inverted rule table with W^T, dW =
+        v3d_sparse_conv_bwd_weight (ops.sparse_conv_backward)."""
         if ctx.fused:
             raise RuntimeError("backward through a BN/ReLU-folded sparse conv is not defined; call .train()")
         features, weight, nbr = ctx.saved_tensors
-        kv = nbr.shape[0]
-        w = weight.reshape(kv, weight.shape[-2], weight.shape[-1])
-        g_feat = torch.zeros_like(features)
-        g_w = torch.zeros_like(w)
-        go = grad_out.contiguous()
-        for kk in range(kv):
-            src = nbr[kk, :ctx.n_out].long()
-            o = torch.nonzero(src >= 0).squeeze(1)
-            if o.numel() == 0:
-                continue
-            i = src[o]
-            g_feat.index_add_(0, i, go[o] @ w[kk].t())
-            g_w[kk] = features[i].t() @ go[o]
-        return g_feat, g_w.reshape(weight.shape), None, None, None, None, None, None
+        g_feat, g_w = ops.sparse_conv_backward(features, weight, nbr, ctx.n_out_dev, ctx.n_out, grad_out.contiguous(),
+                                               ctx.subm, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return g_feat, (g_w.reshape(weight.shape) if g_w is not None else None), None, None, None, None, None, None, None
 
 
 def _triple(v, ndim=3):
@@ -262,7 +253,7 @@ class SparseConvolution(SparseModule):
         feats = _SparseConvFunction.apply(input.features, weight, nbr, n_out_dev, n_out,
                                           scale.detach() if scale is not None else None,
                                           shift.detach() if shift is not None else None,
-                                          bool(fold_relu and fold_bn is not None))
+                                          bool(fold_relu and fold_bn is not None), self.subm)
         out = SparseConvTensor(feats, out_idx, out_shape, input.batch_size)
         out.indice_dict = input.indice_dict if self.subm else {}
         if self.subm:

@@ -144,6 +144,8 @@ int sparse_conv_simt(const float* feat, const float* weight, const int* nbr, int
                      float* out, cudaStream_t st) {
   if (Cin <= 0 || (Cin & 3)) return V3D_ERR_INVALID_ARGUMENT;
   switch (Cout) {
+    case 4: return launch_simt<4>(feat, weight, nbr, nbr_stride, n_out, out_cap, KV, Cin, scale, shift, relu, out, st);
+    case 8: return launch_simt<8>(feat, weight, nbr, nbr_stride, n_out, out_cap, KV, Cin, scale, shift, relu, out, st);
     case 16: return launch_simt<16>(feat, weight, nbr, nbr_stride, n_out, out_cap, KV, Cin, scale, shift, relu, out, st);
     case 32: return launch_simt<32>(feat, weight, nbr, nbr_stride, n_out, out_cap, KV, Cin, scale, shift, relu, out, st);
     case 64: return launch_simt<64>(feat, weight, nbr, nbr_stride, n_out, out_cap, KV, Cin, scale, shift, relu, out, st);

@@ -382,6 +382,47 @@ def sparse_conv(feat, weight, nbr, n_out, out_capacity, scale=None, shift=None, 
     return out
 
 
+def rulebook_invert(nbr, n_out, out_capacity, in_rows):
+    """inv (KV, in_rows) int32 with inv[k][i] = o  <=>  nbr[k][o] = i (else -1): the rule table of the conv's backward
+    w.r.t. its input (for a fixed offset the map is injective)."""
+    kv = nbr.shape[0]
+    inv = torch.empty((kv, max(int(in_rows), 1)), dtype=_I32, device=nbr.device)
+    with torch.cuda.device(nbr.device):
+        check(_lib.load().v3d_rulebook_invert(nbr.data_ptr(), nbr.shape[1], n_out.data_ptr(), int(out_capacity), kv,
+                                              inv.data_ptr(), inv.shape[1], _stream()), "v3d_rulebook_invert")
+    return inv
+
+
+def sparse_conv_backward(feat, weight, nbr, n_out, n_out_host, grad_out, subm, need_input_grad=True, need_weight_grad=True):
+    """Gradients of out = sparse_conv(feat, weight, nbr) (no folded BN / ReLU): (dX (rows, Cin) or None,
+    dW (KV, Cin, Cout) or None). dX runs the forward kernel on the inverted rule table with transposed weights,
+    dW is v3d_sparse_conv_bwd_weight."""
+    cin, cout = weight.shape[-2], weight.shape[-1]
+    kv = weight.numel() // (cin * cout)
+    w = weight.reshape(kv, cin, cout)
+    go = _cuda_f32(grad_out, "grad_out")
+    n_in = feat.shape[0]
+    cap = max(int(n_out_host), 1)
+    if go.shape[0] < cap:
+        go = torch.cat([go, go.new_zeros((cap - go.shape[0], cout))])
+    g_feat = g_w = None
+    if need_input_grad:
+        if subm:  # nbr[k][o] = i  <=>  nbr[KV-1-k][i] = o
+            inv = torch.flip(nbr[:, :n_in], dims=(0,)).contiguous() if nbr.shape[1] >= n_in else None
+        else:
+            inv = rulebook_invert(nbr, n_out, cap, n_in)
+        n_in_dev = torch.full((1,), n_in, dtype=_I32, device=feat.device)
+        g_feat = sparse_conv(go, w.transpose(1, 2).contiguous(), inv, n_in_dev, max(n_in, 1))[:n_in]
+    if need_weight_grad:
+        g_w = torch.empty((kv, cin, cout), dtype=_F32, device=feat.device)
+        f = _cuda_f32(feat, "feat")
+        with torch.cuda.device(feat.device):
+            check(_lib.load().v3d_sparse_conv_bwd_weight(f.data_ptr(), go.data_ptr(), nbr.data_ptr(), nbr.shape[1],
+                                                         n_out.data_ptr(), cap, kv, cin, cout, g_w.data_ptr(), _stream()),
+                  "v3d_sparse_conv_bwd_weight")
+    return g_feat, g_w
+
+
 def sparse_to_dense(feat, indices, n_rows, capacity_rows, batch_size, shape, out=None, workspace=None):
     C = feat.shape[1]
     dev = feat.device
