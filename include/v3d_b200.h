@@ -282,6 +282,19 @@ V3D_API int v3d_ball_query_msg(const float* xyz, int point_stride, const int* ro
                                int B, int N, int M, int n_radii, const float* radii_host,
                                const int* nsamples_host, int* const* idx_host, v3d_stream_t stream);
 
+/* a9 with culling, same results as v3d_ball_query_msg bit for bit: v3d_ball_query_bounds writes one axis-aligned box
+ * per 32 consecutive source rows of every frame into `bounds` (v3d_ball_query_bounds_bytes(B, max_rows_per_frame)
+ * bytes; max_rows_per_frame >= every frame's row count), v3d_ball_query_msg_culled skips the chunks whose box is
+ * farther from the query than the largest radius. Pays off when consecutive rows are spatially close: the sparse
+ * levels produced by strided convolutions are in ascending (b,z,y,x) order. */
+V3D_API size_t v3d_ball_query_bounds_bytes(int B, int max_rows_per_frame);
+V3D_API int v3d_ball_query_bounds(const float* xyz, int point_stride, const int* row_offsets, int B, int N,
+                                  int max_rows_per_frame, void* bounds, v3d_stream_t stream);
+V3D_API int v3d_ball_query_msg_culled(const float* xyz, int point_stride, const int* row_offsets, const void* bounds,
+                                      int max_rows_per_frame, const float* new_xyz, int B, int N, int M, int n_radii,
+                                      const float* radii_host, const int* nsamples_host, int* const* idx_host,
+                                      v3d_stream_t stream);
+
 /* a10 QueryAndGroup(use_xyz=True) reading ROW-major sources: xyz (rows, xyz_stride), feat rows of C floats
  * `feat_stride` floats apart (C may be 0; feat may alias xyz, e.g. the intensity column of (x,y,z,i) points),
  * dense (row = b*N + idx) or ragged (row = row_offsets[b] + idx) -> out[B, 3+C, M, nsample]. Spares the

@@ -145,6 +145,18 @@ def test_point_op_kernels_new_entry_points(cuda):
         for r, (rad, n_) in enumerate(zip([0.8, 1.6], [16, 32])):
             ref = oracle.ball_query(rad, n_, clouds[b][None, :lens[b], :3].copy(), kp4[b:b + 1].cpu().numpy())
             assert np.array_equal(outs[r][b].cpu().numpy(), ref[0]), (b, r)
+    # culled variant (chunk bounding boxes): bit-identical on ragged sources in random order and in sorted order
+    bnd = ops.BallQueryBounds(3, rows.shape[0], cuda).build(rows, offs)
+    culled = ops.ball_query_msg([0.8, 1.6], [16, 32], rows, kp4, offs, bounds=bnd)
+    assert torch.equal(culled[0], outs[0]) and torch.equal(culled[1], outs[1])
+    srt = torch.cat([rows[int(offs[b]):int(offs[b + 1])][torch.argsort(
+        (rows[int(offs[b]):int(offs[b + 1]), 2] * 10).floor() * 1e6 + (rows[int(offs[b]):int(offs[b + 1]), 1] * 10).floor() * 1e3
+        + rows[int(offs[b]):int(offs[b + 1]), 0])] for b in range(3)]).contiguous()
+    plain_s = ops.ball_query_msg([0.3, 2.5], [16, 32], srt, kp4, offs)
+    culled_s = ops.ball_query_msg([0.3, 2.5], [16, 32], srt, kp4, offs, bounds=ops.BallQueryBounds(3, 8192, cuda).build(srt, offs))
+    assert torch.equal(plain_s[0], culled_s[0]) and torch.equal(plain_s[1], culled_s[1])
+    dense_b = ops.BallQueryBounds(3, 8192, cuda).build(pts)
+    assert torch.equal(ops.ball_query_msg([0.4], [16], pts, kp4, bounds=dense_b)[0], ops.ball_query_msg([0.4], [16], pts, kp4)[0])
     feat = torch.randn((rows.shape[0], 5), device=cuda)
     g = ops.query_and_group_rows(rows, feat, kp4, outs[0], offs)
     for b in range(3):

@@ -344,6 +344,119 @@ __global__ void __launch_bounds__(kBqWarps * 32) ball_query_warp_kernel(const fl
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// a9 with hierarchical culling. Every 32 consecutive source rows ("chunk") get an axis-aligned bounding box
+// (bq_bounds_kernel, one warp per chunk). A query warp tests 32 chunk boxes at once (one per lane): the squared
+// distance from the query to a box is a lower bound -- evaluated with the same rounded operations in the same
+// order as dist2, so it is a lower bound in floating point too -- of the distance to every point inside it, so a
+// chunk whose bound is >= r^2 of the largest radius contains no hit and is skipped. Surviving chunks are tested
+// point by point in ascending row order exactly as in ball_query_warp_kernel: the result is bit-identical.
+// Rows of the conv-produced sparse levels are in ascending (b, z, y, x) order, so a chunk is a thin slab (one z,
+// a few y lines) and a ball of 1-5 m meets ~5 % of them; for sources in random order (raw points, level 0) every
+// box spans the scene and the plain kernel is used instead.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bq_bounds_kernel(const float* __restrict__ xyz, int stride, int N,
+                                                        const int* __restrict__ row_offsets, int max_chunks,
+                                                        float4* __restrict__ lo, float4* __restrict__ hi) {
+  const int b = blockIdx.y, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c >= max_chunks) return;
+  int base = b * N, n = N;
+  if (row_offsets) {
+    base = __ldg(&row_offsets[b]);
+    n = __ldg(&row_offsets[b + 1]) - base;
+  }
+  const int r = c * 32 + lane;
+  float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+  if (r < n) {
+    const float* p = xyz + (size_t)(base + r) * stride;
+#pragma unroll
+    for (int d = 0; d < 3; d++) mn[d] = mx[d] = __ldg(&p[d]);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1)
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+      mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+    }
+  if (lane == 0) {
+    lo[(size_t)b * max_chunks + c] = make_float4(mn[0], mn[1], mn[2], 0.f);
+    hi[(size_t)b * max_chunks + c] = make_float4(mx[0], mx[1], mx[2], 0.f);
+  }
+}
+
+template <int R>
+__global__ void __launch_bounds__(kBqWarps * 32) ball_query_cull_kernel(const float* __restrict__ xyz, int stride, int N,
+                                                                        const int* __restrict__ row_offsets,
+                                                                        const float4* __restrict__ lo,
+                                                                        const float4* __restrict__ hi, int max_chunks,
+                                                                        const float* __restrict__ new_xyz, int M, BqArgs A) {
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * kBqWarps + warp;
+  if (q >= M) return;  // (no block-wide barrier in this kernel)
+  int base = b * N, n = N;
+  if (row_offsets) {
+    base = __ldg(&row_offsets[b]);
+    n = __ldg(&row_offsets[b + 1]) - base;
+  }
+  const float* P = xyz + (size_t)base * stride;
+  const float* c = new_xyz + ((size_t)b * M + q) * 3;
+  const float qx = __ldg(c), qy = __ldg(c + 1), qz = __ldg(c + 2);
+  float r2max = 0.f;
+#pragma unroll
+  for (int r = 0; r < R; r++) r2max = fmaxf(r2max, A.r2[r]);
+  int cnt[R], first[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) cnt[r] = 0, first[r] = 0;
+  const unsigned lt = (1u << lane) - 1u;
+  const int n_chunks = (n + 31) >> 5;
+  bool done = false;
+  for (int sc = 0; sc < n_chunks && !done; sc += 32) {
+    const int ci = sc + lane;
+    bool alive = false;
+    if (ci < n_chunks) {
+      const float4 l = __ldg(&lo[(size_t)b * max_chunks + ci]), h = __ldg(&hi[(size_t)b * max_chunks + ci]);
+      // per-axis gap between the query and the box: the same rounded subtraction dist2 performs on a point's
+      // coordinate, applied to the nearest face -> a lower bound of |q - p| on that axis for every p in the box
+      const float gx = fmaxf(fmaxf(__fsub_rn(l.x, qx), __fsub_rn(qx, h.x)), 0.f);
+      const float gy = fmaxf(fmaxf(__fsub_rn(l.y, qy), __fsub_rn(qy, h.y)), 0.f);
+      const float gz = fmaxf(fmaxf(__fsub_rn(l.z, qz), __fsub_rn(qz, h.z)), 0.f);
+      const float bound = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
+      alive = bound < r2max;
+    }
+    unsigned live = __ballot_sync(0xffffffffu, alive);
+    while (live && !done) {
+      const int cc = sc + __ffs(live) - 1;
+      live &= live - 1;
+      const int e = cc * 32 + lane;
+      float d2 = 3.0e38f;
+      if (e < n) {
+        const float* s = P + (size_t)e * stride;
+        d2 = dist2(qx, qy, qz, __ldg(s), __ldg(s + 1), __ldg(s + 2));
+      }
+      bool all_full = true;
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        if (cnt[r] >= A.ns[r]) continue;
+        const bool hit = d2 < A.r2[r];
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (m) {
+          if (cnt[r] == 0) first[r] = cc * 32 + __ffs(m) - 1;
+          const int pos = cnt[r] + __popc(m & lt);
+          if (hit && pos < A.ns[r]) A.out[r][((size_t)b * M + q) * A.ns[r] + pos] = e;
+          cnt[r] += __popc(m);
+        }
+        all_full = all_full && cnt[r] >= A.ns[r];
+      }
+      done = all_full;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; r++)  // unused slots = first hit; no hit at all = zeros (upstream zero-initialises idx)
+    for (int l = min(cnt[r], A.ns[r]) + lane; l < A.ns[r]; l += 32) A.out[r][((size_t)b * M + q) * A.ns[r] + l] = first[r];
+}
+
 // QueryAndGroup on ROW-major sources (what the sparse levels are): out[b, c, q, l] for c < 3 is
 // xyz[row][c] - new_xyz[b, q, c] and feat[row][c - 3] after, row = row_offsets[b] + idx[b, q, l] (or b*N + idx).
 // One thread per (b, q, l) walks the channels: the source row is read once, contiguously.
@@ -569,5 +682,55 @@ extern "C" int v3d_pad_batch(const float* src, int C, const int* row_offsets, in
   const long long want = (total + 255) / 256;
   const int blocks = (int)(want < kNumSMs * 4 ? want : kNumSMs * 4);
   pad_batch_kernel<<<dim3(blocks, B), 256, 0, as_stream(stream)>>>(src, C, row_offsets, frame_capacity, seed, out);
+  return check_launch();
+}
+
+extern "C" size_t v3d_ball_query_bounds_bytes(int B, int max_rows_per_frame) {
+  if (B <= 0 || max_rows_per_frame <= 0) return 0;
+  return (size_t)2 * B * ((max_rows_per_frame + 31) / 32) * sizeof(float4);
+}
+
+extern "C" int v3d_ball_query_bounds(const float* xyz, int point_stride, const int* row_offsets, int B, int N,
+                                     int max_rows_per_frame, void* bounds, v3d_stream_t stream) {
+  if (!xyz || !bounds || B <= 0 || B > 65535 || point_stride < 3 || max_rows_per_frame <= 0) return V3D_ERR_INVALID_ARGUMENT;
+  if (!row_offsets && (N <= 0 || N > max_rows_per_frame)) return V3D_ERR_INVALID_ARGUMENT;
+  const int max_chunks = (max_rows_per_frame + 31) / 32;
+  float4* lo = static_cast<float4*>(bounds);
+  float4* hi = lo + (size_t)B * max_chunks;
+  bq_bounds_kernel<<<dim3(ceil_div(max_chunks, 8), B), 256, 0, as_stream(stream)>>>(xyz, point_stride, N, row_offsets,
+                                                                                  max_chunks, lo, hi);
+  return check_launch();
+}
+
+extern "C" int v3d_ball_query_msg_culled(const float* xyz, int point_stride, const int* row_offsets, const void* bounds,
+                                         int max_rows_per_frame, const float* new_xyz, int B, int N, int M, int n_radii,
+                                         const float* radii_host, const int* nsamples_host, int* const* idx_host,
+                                         v3d_stream_t stream) {
+  if (!xyz || !new_xyz || !bounds || !radii_host || !nsamples_host || !idx_host) return V3D_ERR_INVALID_ARGUMENT;
+  if (B <= 0 || B > 65535 || M <= 0 || n_radii <= 0 || n_radii > kBqMaxR || point_stride < 3 || max_rows_per_frame <= 0)
+    return V3D_ERR_INVALID_ARGUMENT;
+  if (!row_offsets && (N <= 0 || N > max_rows_per_frame)) return V3D_ERR_INVALID_ARGUMENT;
+  BqArgs A;
+  for (int r = 0; r < kBqMaxR; r++) {
+    const int s = r < n_radii ? r : 0;
+    if (nsamples_host[s] <= 0 || !idx_host[s]) return V3D_ERR_INVALID_ARGUMENT;
+    A.r2[r] = radii_host[s] * radii_host[s];
+    A.ns[r] = nsamples_host[s];
+    A.out[r] = idx_host[s];
+  }
+  const int max_chunks = (max_rows_per_frame + 31) / 32;
+  const float4* lo = static_cast<const float4*>(bounds);
+  const float4* hi = lo + (size_t)B * max_chunks;
+  dim3 grid(ceil_div(M, kBqWarps), B);
+  cudaStream_t st = as_stream(stream);
+#define V3D_BQC(RR) \
+  ball_query_cull_kernel<RR><<<grid, kBqWarps * 32, 0, st>>>(xyz, point_stride, N, row_offsets, lo, hi, max_chunks, new_xyz, M, A)
+  switch (n_radii) {
+    case 1: V3D_BQC(1); break;
+    case 2: V3D_BQC(2); break;
+    case 3: V3D_BQC(3); break;
+    default: V3D_BQC(4); break;
+  }
+#undef V3D_BQC
   return check_launch();
 }

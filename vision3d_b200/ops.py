@@ -546,7 +546,28 @@ def fps_keypoints(points, npoint, idx=None, keypoints=None):
     return idx, keypoints
 
 
-def ball_query_msg(radii, nsamples, xyz, new_xyz, row_offsets=None, out=None):
+class BallQueryBounds:
+    """Per-chunk bounding boxes of a source (32 consecutive rows per box) for the culled ball query. Build once per
+    source with `.build(xyz, row_offsets)`, pass as `bounds=` to ball_query_msg. `max_rows_per_frame` bounds every
+    frame's row count (for ragged sources: the level's total row capacity is always safe)."""
+
+    def __init__(self, batch_size, max_rows_per_frame, device):
+        self.B, self.max_rows = int(batch_size), int(max_rows_per_frame)
+        nbytes = _lib.load().v3d_ball_query_bounds_bytes(self.B, self.max_rows)
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+    def build(self, xyz, row_offsets=None):
+        x = _cuda_f32(xyz, "xyz")
+        N = x.shape[1] if row_offsets is None else 0
+        with torch.cuda.device(x.device):
+            check(_lib.load().v3d_ball_query_bounds(x.data_ptr(), x.shape[-1],
+                                                    row_offsets.data_ptr() if row_offsets is not None else None, self.B,
+                                                    N, self.max_rows, self.buf.data_ptr(), _stream()),
+                  "v3d_ball_query_bounds")
+        return self
+
+
+def ball_query_msg(radii, nsamples, xyz, new_xyz, row_offsets=None, out=None, bounds=None):
     """All ball queries of one PointnetSAModuleMSG in one pass. xyz: dense (B, N, S>=3) or, with `row_offsets`
     (B+1 int32 device), packed (rows, S) ragged sources (indices relative to the frame start). new_xyz (B, M, 3).
     Returns [idx_r (B, M, ns_r) int32 ...]."""
@@ -562,6 +583,11 @@ def ball_query_msg(radii, nsamples, xyz, new_xyz, row_offsets=None, out=None):
     nsa = (ctypes.c_int * R)(*[int(n) for n in nsamples])
     ptrs = (ctypes.c_void_p * R)(*[o.data_ptr() for o in out])
     with torch.cuda.device(x.device):
+        if bounds is not None:  # culled variant: bit-identical results, skips chunks of 32 rows far from the query
+            check(_lib.load().v3d_ball_query_msg_culled(
+                x.data_ptr(), S, row_offsets.data_ptr() if row_offsets is not None else None, bounds.buf.data_ptr(),
+                bounds.max_rows, q.data_ptr(), B, N, M, R, rad, nsa, ptrs, _stream()), "v3d_ball_query_msg_culled")
+            return out
         check(_lib.load().v3d_ball_query_msg(x.data_ptr(), S, row_offsets.data_ptr() if row_offsets is not None else None,
                                              q.data_ptr(), B, N, M, R, rad, nsa, ptrs, _stream()), "v3d_ball_query_msg")
     return out

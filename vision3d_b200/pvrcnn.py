@@ -243,6 +243,8 @@ class KeypointStage:
                        for _ in range(5)]
         Mg = self.n * cfg.GRIDPOOL_NUM_GRIDPOINTS
         self.roi_idx = [torch.zeros((B, Mg, ns), dtype=torch.int32, device=dev) for ns in cfg.SAMPLES_PN]
+        # levels 1-3 are in ascending (b,z,y,x) order: chunk bounding boxes make their ball queries ~20x cheaper
+        self.sa_bounds = [None, None] + [ops.BallQueryBounds(B, self.eng.caps[lv], dev) for lv in (1, 2, 3)]
         self.kp_features = torch.zeros((B, 512, M), dtype=torch.float32, device=dev)
         # fused set abstraction: grouping -> shared MLP -> max in one tensor-core kernel per scale
         self.fused_sa = bool(fused_sa)
@@ -281,7 +283,8 @@ class KeypointStage:
     def _sa_query(self, i):
         xyz, _, offs = self._source(i)
         radii = [g.radius for g in self.model.pnets[i].groupers]
-        ops.ball_query_msg(radii, self.cfg.SAMPLES_PN, xyz, self.keypoints, offs, out=self.sa_idx[i])
+        bounds = self.sa_bounds[i].build(xyz, offs) if self.sa_bounds[i] is not None else None
+        ops.ball_query_msg(radii, self.cfg.SAMPLES_PN, xyz, self.keypoints, offs, out=self.sa_idx[i], bounds=bounds)
 
     def _sa_group(self, i, r):
         xyz, feat, offs = self._source(i)
