@@ -20,15 +20,15 @@ def short(name):
     return (m.group(1) if m else name)[:80]
 
 
-def launches(path):
+def launches(path, first_kernel="vox_insert"):
     txt = open(path).read()
     rows = list(csv.DictReader(io.StringIO(txt[txt.index('"ID"'):])))
     names = [short(r["Kernel Name"]) for r in rows]
-    starts = [i for i, n in enumerate(names) if "vox_insert" in n]
+    starts = [i for i, n in enumerate(names) if first_kernel in n]
     a, b = (starts[0], starts[1]) if len(starts) > 1 else (0, len(rows))
     step = rows[a:b]
     tot = sum(float(r["Metric Value"]) for r in step) / 1e3
-    print("# ncu launch list, one SECOND step (batch 16), gpu__time_duration.sum per launch")
+    print("# ncu launch list, one step (first kernel: %s), gpu__time_duration.sum per launch" % first_kernel)
     print("# cold-cache, serialised launches: compare SHARES, not absolutes. step total = %.1f us, %d launches\n"
           % (tot, len(step)))
     agg = collections.OrderedDict()
