@@ -295,6 +295,21 @@ V3D_API int v3d_ball_query_msg_culled(const float* xyz, int point_stride, const 
                                       const float* radii_host, const int* nsamples_host, int* const* idx_host,
                                       v3d_stream_t stream);
 
+/* a9 for sources whose rows are NOT spatially ordered (shuffled raw points, first-appearance voxels), same results bit
+ * for bit: v3d_ball_query_sort_x buckets every frame's rows along x into `sorted` (float4 rows {x, y, z, original row
+ * index}; same frame ranges as the source; workspace of v3d_ball_query_sort_workspace_bytes(B) bytes, zeroed once),
+ * v3d_ball_query_bounds on `sorted` (stride 4) gives thin chunk boxes, and v3d_ball_query_msg_select culls with them
+ * and keeps, per radius, the nsample (<= 32) smallest ORIGINAL indices among the hits = the first nsample hits of the
+ * reference's index-order scan. x_min / x_max: the extent of the scene along x (values outside are clamped). */
+V3D_API size_t v3d_ball_query_sort_workspace_bytes(int B);
+V3D_API int v3d_ball_query_sort_x(const float* xyz, int point_stride, const int* row_offsets, int B, int N,
+                                  int max_rows_per_frame, float x_min, float x_max, void* sorted, void* workspace,
+                                  v3d_stream_t stream);
+V3D_API int v3d_ball_query_msg_select(const void* sorted, const int* row_offsets, const void* bounds,
+                                      int max_rows_per_frame, const float* new_xyz, int B, int N, int M, int n_radii,
+                                      const float* radii_host, const int* nsamples_host, int* const* idx_host,
+                                      v3d_stream_t stream);
+
 /* a10 QueryAndGroup(use_xyz=True) reading ROW-major sources: xyz (rows, xyz_stride), feat rows of C floats
  * `feat_stride` floats apart (C may be 0; feat may alias xyz, e.g. the intensity column of (x,y,z,i) points),
  * dense (row = b*N + idx) or ragged (row = row_offsets[b] + idx) -> out[B, 3+C, M, nsample]. Spares the

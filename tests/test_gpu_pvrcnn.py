@@ -157,6 +157,20 @@ def test_point_op_kernels_new_entry_points(cuda):
     assert torch.equal(plain_s[0], culled_s[0]) and torch.equal(plain_s[1], culled_s[1])
     dense_b = ops.BallQueryBounds(3, 8192, cuda).build(pts)
     assert torch.equal(ops.ball_query_msg([0.4], [16], pts, kp4, bounds=dense_b)[0], ops.ball_query_msg([0.4], [16], pts, kp4)[0])
+    # selecting variant (x-bucketed copy + nsample smallest original indices): bit-identical, ragged and dense,
+    # dense balls (many more hits than nsample), points outside the x range (clamped buckets), nsample < 16
+    sel = ops.BallQuerySorted(3, rows.shape[0], rows.shape[0], (0.0, 70.4), cuda).build(rows, offs)
+    got = sel.query([0.8, 1.6], [16, 32], kp4)
+    assert torch.equal(got[0], outs[0]) and torch.equal(got[1], outs[1])
+    got = sel.query([0.3, 2.5, 6.0], [5, 32, 32], kp4)
+    want = ops.ball_query_msg([0.3, 2.5, 6.0], [5, 32, 32], rows, kp4, offs)
+    assert all(torch.equal(a, b) for a, b in zip(got, want))
+    seld = ops.BallQuerySorted(3, 8192, 3 * 8192, (10.0, 30.0), cuda).build(pts)     # stride-4 dense rows, narrow range
+    got = seld.query([0.4, 3.0], [16, 32], kp4)
+    want = ops.ball_query_msg([0.4, 3.0], [16, 32], pts, kp4)
+    assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+    got2 = seld.build(pts).query([0.4, 3.0], [16, 32], kp4)                          # workspace re-armed by the scan
+    assert torch.equal(got2[0], want[0]) and torch.equal(got2[1], want[1])
     feat = torch.randn((rows.shape[0], 5), device=cuda)
     g = ops.query_and_group_rows(rows, feat, kp4, outs[0], offs)
     for b in range(3):

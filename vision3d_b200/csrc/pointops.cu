@@ -457,6 +457,140 @@ __global__ void __launch_bounds__(kBqWarps * 32) ball_query_cull_kernel(const fl
     for (int l = min(cnt[r], A.ns[r]) + lane; l < A.ns[r]; l += 32) A.out[r][((size_t)b * M + q) * A.ns[r] + l] = first[r];
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// a9 for sources in RANDOM row order (raw points are shuffled, level-0 voxels are in first-appearance order): chunk
+// boxes of consecutive rows span the whole scene, so the culled kernel above cannot skip anything. Here the rows of
+// every frame are first bucketed along x (counting sort into 0.25 m slabs: histogram, scan, scatter -- the order
+// INSIDE a slab is whatever the atomics produce, which does not matter, see below) into float4 rows
+// {x, y, z, original index}; chunk boxes of the bucketed rows are thin in x and the same box test skips ~97 % of
+// them. The reference semantics "the first nsample hits in ascending ORIGINAL index order" is then a selection
+// problem: a query warp keeps, per radius, the nsample smallest original indices among all hits in a sorted
+// register array (one entry per lane), inserting a new hit only when it beats the current worst. The hit set is
+// the same (same rounded distance test) and the nsample smallest indices of a set do not depend on the order the
+// set is enumerated in, so the result is bit-identical to the sequential scan -- and deterministic although the
+// bucketing is not.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kBsMaxBuckets = 1024;
+
+__global__ void __launch_bounds__(256) bs_hist_kernel(const float* __restrict__ xyz, int stride, int N,
+                                                      const int* __restrict__ row_offsets, float x0, float inv_w,
+                                                      int n_buckets, int* __restrict__ cnt) {
+  const int b = blockIdx.y;
+  int base = b * N, n = N;
+  if (row_offsets) {
+    base = __ldg(&row_offsets[b]);
+    n = __ldg(&row_offsets[b + 1]) - base;
+  }
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+    const float x = __ldg(&xyz[(size_t)(base + r) * stride]);
+    const int k = min(max((int)floorf((x - x0) * inv_w), 0), n_buckets - 1);
+    atomicAdd(&cnt[b * kBsMaxBuckets + k], 1);
+  }
+}
+
+__global__ void __launch_bounds__(kBsMaxBuckets) bs_scan_kernel(int* __restrict__ cnt, int* __restrict__ cursor) {
+  __shared__ int sm[33];
+  const int b = blockIdx.x;
+  const int v = cnt[b * kBsMaxBuckets + threadIdx.x];
+  int total;
+  const int ex = block_exclusive_scan(v, sm, total);
+  cursor[b * kBsMaxBuckets + threadIdx.x] = ex;
+  cnt[b * kBsMaxBuckets + threadIdx.x] = 0;  // ready for the next call
+}
+
+__global__ void __launch_bounds__(256) bs_scatter_kernel(const float* __restrict__ xyz, int stride, int N,
+                                                         const int* __restrict__ row_offsets, float x0, float inv_w,
+                                                         int n_buckets, int* __restrict__ cursor,
+                                                         float4* __restrict__ sorted) {
+  const int b = blockIdx.y;
+  int base = b * N, n = N;
+  if (row_offsets) {
+    base = __ldg(&row_offsets[b]);
+    n = __ldg(&row_offsets[b + 1]) - base;
+  }
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+    const float* p = xyz + (size_t)(base + r) * stride;
+    const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+    const int k = min(max((int)floorf((x - x0) * inv_w), 0), n_buckets - 1);
+    const int pos = atomicAdd(&cursor[b * kBsMaxBuckets + k], 1);
+    sorted[(size_t)base + pos] = make_float4(x, y, z, __int_as_float(r));
+  }
+}
+
+template <int R>
+__global__ void __launch_bounds__(kBqWarps * 32) ball_query_select_kernel(const float4* __restrict__ sorted, int N,
+                                                                          const int* __restrict__ row_offsets,
+                                                                          const float4* __restrict__ lo,
+                                                                          const float4* __restrict__ hi, int max_chunks,
+                                                                          const float* __restrict__ new_xyz, int M, BqArgs A) {
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * kBqWarps + warp;
+  if (q >= M) return;
+  int base = b * N, n = N;
+  if (row_offsets) {
+    base = __ldg(&row_offsets[b]);
+    n = __ldg(&row_offsets[b + 1]) - base;
+  }
+  const float4* P = sorted + base;
+  const float* c = new_xyz + ((size_t)b * M + q) * 3;
+  const float qx = __ldg(c), qy = __ldg(c + 1), qz = __ldg(c + 2);
+  float r2max = 0.f;
+#pragma unroll
+  for (int r = 0; r < R; r++) r2max = fmaxf(r2max, A.r2[r]);
+  constexpr int kNone = 0x7fffffff;
+  int best[R];  // lane l: the l-th smallest original index among the hits of radius r seen so far (l < ns[r])
+#pragma unroll
+  for (int r = 0; r < R; r++) best[r] = kNone;
+  const int n_chunks = (n + 31) >> 5;
+  for (int sc = 0; sc < n_chunks; sc += 32) {
+    const int ci = sc + lane;
+    bool alive = false;
+    if (ci < n_chunks) {
+      const float4 l = __ldg(&lo[(size_t)b * max_chunks + ci]), h = __ldg(&hi[(size_t)b * max_chunks + ci]);
+      const float gx = fmaxf(fmaxf(__fsub_rn(l.x, qx), __fsub_rn(qx, h.x)), 0.f);
+      const float gy = fmaxf(fmaxf(__fsub_rn(l.y, qy), __fsub_rn(qy, h.y)), 0.f);
+      const float gz = fmaxf(fmaxf(__fsub_rn(l.z, qz), __fsub_rn(qz, h.z)), 0.f);
+      alive = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz)) < r2max;
+    }
+    unsigned live = __ballot_sync(0xffffffffu, alive);
+    while (live) {
+      const int cc = sc + __ffs(live) - 1;
+      live &= live - 1;
+      const int e = cc * 32 + lane;
+      float d2 = 3.0e38f;
+      int oi = kNone;
+      if (e < n) {
+        const float4 p = __ldg(&P[e]);
+        d2 = dist2(qx, qy, qz, p.x, p.y, p.z);
+        oi = __float_as_int(p.w);
+      }
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        unsigned m = __ballot_sync(0xffffffffu, d2 < A.r2[r]);
+        while (m) {
+          const int src = __ffs(m) - 1;
+          m &= m - 1;
+          const int v = __shfl_sync(0xffffffffu, oi, src);
+          const int worst = __shfl_sync(0xffffffffu, best[r], A.ns[r] - 1);
+          if (v < worst) {  // (warp-uniform) insert v, dropping the current worst
+            const int pos = __popc(__ballot_sync(0xffffffffu, best[r] < v));  // entries are sorted: a prefix is smaller
+            const int up = __shfl_up_sync(0xffffffffu, best[r], 1);
+            if (lane >= pos) best[r] = lane == pos ? v : up;
+            if (lane >= A.ns[r]) best[r] = kNone;
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const int cnt = __popc(__ballot_sync(0xffffffffu, best[r] != kNone));
+    const int first = __shfl_sync(0xffffffffu, best[r], 0);
+    if (lane < A.ns[r])  // unused slots = first hit; no hit at all = zeros (upstream zero-initialises idx)
+      A.out[r][((size_t)b * M + q) * A.ns[r] + lane] = lane < cnt ? best[r] : (cnt > 0 ? first : 0);
+  }
+}
+
 // QueryAndGroup on ROW-major sources (what the sparse levels are): out[b, c, q, l] for c < 3 is
 // xyz[row][c] - new_xyz[b, q, c] and feat[row][c - 3] after, row = row_offsets[b] + idx[b, q, l] (or b*N + idx).
 // One thread per (b, q, l) walks the channels: the source row is read once, contiguously.
@@ -732,5 +866,60 @@ extern "C" int v3d_ball_query_msg_culled(const float* xyz, int point_stride, con
     default: V3D_BQC(4); break;
   }
 #undef V3D_BQC
+  return check_launch();
+}
+
+// Bucketed copy of a source for v3d_ball_query_msg_select: `sorted` = float4 rows {x, y, z, original row index within
+// the frame} (same frame ranges as the source), `workspace` = 2 * B * 1024 ints (zero-initialised once by the caller).
+extern "C" size_t v3d_ball_query_sort_workspace_bytes(int B) { return B > 0 ? (size_t)2 * B * kBsMaxBuckets * sizeof(int) : 0; }
+
+extern "C" int v3d_ball_query_sort_x(const float* xyz, int point_stride, const int* row_offsets, int B, int N,
+                                     int max_rows_per_frame, float x_min, float x_max, void* sorted, void* workspace,
+                                     v3d_stream_t stream) {
+  if (!xyz || !sorted || !workspace || B <= 0 || B > 65535 || point_stride < 3 || max_rows_per_frame <= 0 || !(x_max > x_min))
+    return V3D_ERR_INVALID_ARGUMENT;
+  if (!row_offsets && (N <= 0 || N > max_rows_per_frame)) return V3D_ERR_INVALID_ARGUMENT;
+  int* cnt = static_cast<int*>(workspace);
+  int* cursor = cnt + (size_t)B * kBsMaxBuckets;
+  const float inv_w = (float)kBsMaxBuckets / (x_max - x_min);
+  cudaStream_t st = as_stream(stream);
+  const int blocks = ceil_div(max_rows_per_frame, 256) < 64 ? ceil_div(max_rows_per_frame, 256) : 64;
+  bs_hist_kernel<<<dim3(blocks, B), 256, 0, st>>>(xyz, point_stride, N, row_offsets, x_min, inv_w, kBsMaxBuckets, cnt);
+  bs_scan_kernel<<<B, kBsMaxBuckets, 0, st>>>(cnt, cursor);
+  bs_scatter_kernel<<<dim3(blocks, B), 256, 0, st>>>(xyz, point_stride, N, row_offsets, x_min, inv_w, kBsMaxBuckets, cursor,
+                                                     static_cast<float4*>(sorted));
+  return check_launch();
+}
+
+extern "C" int v3d_ball_query_msg_select(const void* sorted, const int* row_offsets, const void* bounds,
+                                         int max_rows_per_frame, const float* new_xyz, int B, int N, int M, int n_radii,
+                                         const float* radii_host, const int* nsamples_host, int* const* idx_host,
+                                         v3d_stream_t stream) {
+  if (!sorted || !new_xyz || !bounds || !radii_host || !nsamples_host || !idx_host) return V3D_ERR_INVALID_ARGUMENT;
+  if (B <= 0 || B > 65535 || M <= 0 || n_radii <= 0 || n_radii > kBqMaxR || max_rows_per_frame <= 0) return V3D_ERR_INVALID_ARGUMENT;
+  if (!row_offsets && (N <= 0 || N > max_rows_per_frame)) return V3D_ERR_INVALID_ARGUMENT;
+  BqArgs A;
+  for (int r = 0; r < kBqMaxR; r++) {
+    const int s = r < n_radii ? r : 0;
+    if (nsamples_host[s] <= 0 || nsamples_host[s] > 32 || !idx_host[s]) return V3D_ERR_INVALID_ARGUMENT;
+    A.r2[r] = radii_host[s] * radii_host[s];
+    A.ns[r] = nsamples_host[s];
+    A.out[r] = idx_host[s];
+  }
+  const int max_chunks = (max_rows_per_frame + 31) / 32;
+  const float4* lo = static_cast<const float4*>(bounds);
+  const float4* hi = lo + (size_t)B * max_chunks;
+  dim3 grid(ceil_div(M, kBqWarps), B);
+  cudaStream_t st = as_stream(stream);
+#define V3D_BQS(RR)                                                                                              \
+  ball_query_select_kernel<RR><<<grid, kBqWarps * 32, 0, st>>>(static_cast<const float4*>(sorted), N, row_offsets, lo, hi, \
+                                                               max_chunks, new_xyz, M, A)
+  switch (n_radii) {
+    case 1: V3D_BQS(1); break;
+    case 2: V3D_BQS(2); break;
+    case 3: V3D_BQS(3); break;
+    default: V3D_BQS(4); break;
+  }
+#undef V3D_BQS
   return check_launch();
 }

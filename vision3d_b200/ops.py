@@ -567,6 +567,48 @@ class BallQueryBounds:
         return self
 
 
+class BallQuerySorted:
+    """x-bucketed copy of a source in random row order + its chunk boxes, for the selecting ball query
+    (v3d_ball_query_sort_x / _bounds / _msg_select): `.build(xyz, row_offsets)` once per step, then
+    `.query(radii, nsamples, new_xyz, out)`; results are bit-identical to ball_query_msg on the original rows."""
+
+    def __init__(self, batch_size, max_rows_per_frame, total_rows, x_range, device):
+        self.B, self.max_rows, self.x_range = int(batch_size), int(max_rows_per_frame), (float(x_range[0]), float(x_range[1]))
+        self.sorted = torch.zeros((int(total_rows), 4), dtype=_F32, device=device)
+        self.ws = torch.zeros(_lib.load().v3d_ball_query_sort_workspace_bytes(self.B), dtype=torch.uint8, device=device)
+        self.bounds = BallQueryBounds(self.B, self.max_rows, device)
+        self.row_offsets, self.N = None, 0
+
+    def build(self, xyz, row_offsets=None):
+        x = _cuda_f32(xyz, "xyz")
+        self.row_offsets, self.N = row_offsets, (x.shape[1] if row_offsets is None else 0)
+        with torch.cuda.device(x.device):
+            check(_lib.load().v3d_ball_query_sort_x(x.data_ptr(), x.shape[-1],
+                                                    row_offsets.data_ptr() if row_offsets is not None else None, self.B,
+                                                    self.N, self.max_rows, self.x_range[0], self.x_range[1],
+                                                    self.sorted.data_ptr(), self.ws.data_ptr(), _stream()),
+                  "v3d_ball_query_sort_x")
+        view = self.sorted if row_offsets is not None else self.sorted[: self.B * self.N].view(self.B, self.N, 4)
+        self.bounds.build(view, row_offsets)
+        return self
+
+    def query(self, radii, nsamples, new_xyz, out=None):
+        q = _cuda_f32(new_xyz, "new_xyz", 3)
+        B, M, _ = q.shape
+        R = len(radii)
+        if out is None:
+            out = [torch.empty((B, M, int(ns)), dtype=_I32, device=q.device) for ns in nsamples]
+        rad = (ctypes.c_float * R)(*[float(r) for r in radii])
+        nsa = (ctypes.c_int * R)(*[int(n) for n in nsamples])
+        ptrs = (ctypes.c_void_p * R)(*[o.data_ptr() for o in out])
+        with torch.cuda.device(q.device):
+            check(_lib.load().v3d_ball_query_msg_select(
+                self.sorted.data_ptr(), self.row_offsets.data_ptr() if self.row_offsets is not None else None,
+                self.bounds.buf.data_ptr(), self.max_rows, q.data_ptr(), B, self.N, M, R, rad, nsa, ptrs, _stream()),
+                "v3d_ball_query_msg_select")
+        return out
+
+
 def ball_query_msg(radii, nsamples, xyz, new_xyz, row_offsets=None, out=None, bounds=None):
     """All ball queries of one PointnetSAModuleMSG in one pass. xyz: dense (B, N, S>=3) or, with `row_offsets`
     (B+1 int32 device), packed (rows, S) ragged sources (indices relative to the frame start). new_xyz (B, M, 3).

@@ -245,6 +245,10 @@ class KeypointStage:
         self.roi_idx = [torch.zeros((B, Mg, ns), dtype=torch.int32, device=dev) for ns in cfg.SAMPLES_PN]
         # levels 1-3 are in ascending (b,z,y,x) order: chunk bounding boxes make their ball queries ~20x cheaper
         self.sa_bounds = [None, None] + [ops.BallQueryBounds(B, self.eng.caps[lv], dev) for lv in (1, 2, 3)]
+        # raw points (shuffled) and level-0 voxels (first-appearance order): x-bucketed copy + index selection
+        xr = (cfg.GRID_BOUNDS[0], cfg.GRID_BOUNDS[3])
+        self.sa_sorted = [ops.BallQuerySorted(B, self.N, B * self.N, xr, dev),
+                          ops.BallQuerySorted(B, self.eng.caps[0], self.eng.caps[0], xr, dev)]
         self.kp_features = torch.zeros((B, 512, M), dtype=torch.float32, device=dev)
         # fused set abstraction: grouping -> shared MLP -> max in one tensor-core kernel per scale
         self.fused_sa = bool(fused_sa)
@@ -283,6 +287,9 @@ class KeypointStage:
     def _sa_query(self, i):
         xyz, _, offs = self._source(i)
         radii = [g.radius for g in self.model.pnets[i].groupers]
+        if i < 2:
+            self.sa_sorted[i].build(xyz, offs).query(radii, self.cfg.SAMPLES_PN, self.keypoints, out=self.sa_idx[i])
+            return
         bounds = self.sa_bounds[i].build(xyz, offs) if self.sa_bounds[i] is not None else None
         ops.ball_query_msg(radii, self.cfg.SAMPLES_PN, xyz, self.keypoints, offs, out=self.sa_idx[i], bounds=bounds)
 
