@@ -171,6 +171,154 @@ __global__ void __cluster_dims__(kFpsCluster, 1, 1) __launch_bounds__(kFpsThread
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// FPS, direct exchange (clouds of <= 16 384 points, i.e. every configuration the reference runs): the step above
+// costs ~2 100 clk, most of it the block barrier + cluster barrier pair around the candidate exchange, not the
+// distance updates. Here a step has NO barrier at all:
+//   * every CTA of the cluster keeps a copy of the whole cloud's coordinates in shared memory (3 x 64 KB), so a
+//     candidate is fully described by (distance bits, point index) and fits, with a 16-bit step tag, in ONE 64-bit
+//     word -- a single-copy-atomic store, no ordering between a payload and a flag to enforce;
+//   * every WARP reduces its points (2 REDUX) and stores its word into its slot in all 8 CTAs (lanes 0-7, one
+//     remote store each); every warp then polls the local slots (4 warps x 8 CTAs = 32: one per lane) until all
+//     carry this step's tag, reduces them (2 REDUX) and reads the winner's coordinates from its CTA's copy of the
+//     cloud. Measured: 760 clk per step against 2 100 (B = 8, N = 16 384, m = 2 048: 0.82 ms against 2.30 ms).
+// Slots are double-buffered by step parity. A slot of parity p is rewritten at step j+2 by a warp that has seen
+// ALL step j+1 words, and a warp sends its step j+1 word only after it has read the step j slots -- so nobody can
+// still be reading what is overwritten. Results are identical to the kernel above (same distances, same
+// lowest-index tie rule).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kFpsDirectMaxN = 16384;
+
+template <int PPT, int WARPS, int CLUSTER>
+__global__ void __launch_bounds__(WARPS * 32)
+    fps_direct_kernel(const float* __restrict__ xyz, int stride, int N, int n_pad, int m, int* __restrict__ out,
+                      float* __restrict__ out_xyz) {
+  constexpr int kThreads = WARPS * 32;
+  constexpr int kSlots = WARPS * CLUSTER;  // one per warp of the cluster
+  constexpr int SL = kSlots / 32;          // slots polled per lane
+  static_assert(kSlots % 32 == 0 && (SL == 1 || SL == 2 || SL == 4), "slot count");
+  extern __shared__ __align__(16) unsigned char fps_smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int b = blockIdx.x / CLUSTER;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* P = xyz + (size_t)b * N * stride;
+  unsigned long long* slots = reinterpret_cast<unsigned long long*>(fps_smem);  // [2][kSlots]
+  float* sx = reinterpret_cast<float*>(fps_smem + 2 * kSlots * sizeof(unsigned long long));
+  float* sy = sx + n_pad;
+  float* sz = sy + n_pad;
+
+  for (int i = tid; i < N; i += kThreads) {
+    if (stride == 4) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(P) + i);
+      sx[i] = q.x;
+      sy[i] = q.y;
+      sz[i] = q.z;
+    } else {
+      sx[i] = P[(size_t)3 * i];
+      sy[i] = P[(size_t)3 * i + 1];
+      sz[i] = P[(size_t)3 * i + 2];
+    }
+  }
+  for (int i = tid; i < 2 * kSlots; i += kThreads) slots[i] = 0ull;  // tag 0 is never waited for (j starts at 1)
+  __syncthreads();
+  const int s0 = rank * PPT * kThreads;
+  float px[PPT], py[PPT], pz[PPT], md[PPT];
+#pragma unroll
+  for (int k = 0; k < PPT; k++) {
+    const int i = s0 + tid + k * kThreads;
+    const bool ok = i < N;
+    px[k] = ok ? sx[i] : 0.f;
+    py[k] = ok ? sy[i] : 0.f;
+    pz[k] = ok ? sz[i] : 0.f;
+    md[k] = ok ? 1e10f : -1.f;
+  }
+  float cx = sx[0], cy = sy[0], cz = sz[0];
+  if (rank == 0 && tid == 0) {
+    out[(size_t)b * m] = 0;
+    if (out_xyz) {
+      out_xyz[(size_t)b * m * 3] = cx;
+      out_xyz[(size_t)b * m * 3 + 1] = cy;
+      out_xyz[(size_t)b * m * 3 + 2] = cz;
+    }
+  }
+  cluster.sync();  // every CTA's slots are zeroed before the first remote store can land
+
+  unsigned long long* my_remote = cluster.map_shared_rank(slots, lane & (CLUSTER - 1));
+  const int my_slot = rank * WARPS + warp;
+  for (int j = 1; j < m; j++) {
+    const int par = j & 1;
+    const unsigned int tag = (unsigned int)j & 0xffffu;
+    float bd = -1.f;
+    int bk = 0;
+#pragma unroll
+    for (int k = 0; k < PPT; k++) {
+      const float d = dist2(px[k], py[k], pz[k], cx, cy, cz);
+      const float d2 = fminf(d, md[k]);
+      md[k] = d2;
+      if (d2 > bd) {
+        bd = d2;
+        bk = k;
+      }
+    }
+    // (distance bits, 0xffff - index): max = farthest point, lowest index on ties; "no point" = (0, 0) never beats a point
+    unsigned int d = bd < 0.f ? 0u : __float_as_uint(bd);
+    unsigned int n = bd < 0.f ? 0u : 0xffffu - (unsigned int)(s0 + tid + bk * kThreads);
+    warp_argmax(d, n);
+    if (lane < CLUSTER)
+      *reinterpret_cast<volatile unsigned long long*>(my_remote + par * kSlots + my_slot) =
+          ((unsigned long long)d << 32) | (unsigned long long)((n << 16) | tag);
+    // all words of this step, SL per lane
+    const unsigned int a = (unsigned int)__cvta_generic_to_shared(slots + par * kSlots + SL * lane);
+    unsigned long long w0, w1 = 0ull, w2 = 0ull, w3 = 0ull;
+    unsigned int spins = 0;
+    for (;;) {
+      bool ready;
+      if (SL == 1) {
+        asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(w0) : "r"(a));
+        ready = ((unsigned int)w0 & 0xffffu) == tag;
+      } else {
+        asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "r"(a));
+        ready = (((unsigned int)w0 & 0xffffu) == tag) & (((unsigned int)w1 & 0xffffu) == tag);
+        if (SL == 4) {
+          asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(w2), "=l"(w3) : "r"(a + 16));
+          ready = ready & (((unsigned int)w2 & 0xffffu) == tag) & (((unsigned int)w3 & 0xffffu) == tag);
+        }
+      }
+      if (__all_sync(0xffffffffu, ready)) break;
+      if (++spins > (1u << 26)) __trap();  // a lost word would otherwise hang the GPU: fail loudly instead
+    }
+    w0 >>= 16;
+    if (SL >= 2) {
+      w1 >>= 16;
+      w0 = w0 > w1 ? w0 : w1;
+    }
+    if (SL == 4) {
+      w2 >>= 16;
+      w3 >>= 16;
+      w2 = w2 > w3 ? w2 : w3;
+      w0 = w0 > w2 ? w0 : w2;
+    }
+    d = (unsigned int)(w0 >> 16);
+    n = (unsigned int)w0 & 0xffffu;
+    warp_argmax(d, n);
+    const int win = (int)(0xffffu - n);
+    cx = sx[win];
+    cy = sy[win];
+    cz = sz[win];
+    if (rank == 0 && tid == 0) {
+      out[(size_t)b * m + j] = win;
+      if (out_xyz) {
+        float* o = out_xyz + ((size_t)b * m + j) * 3;
+        o[0] = cx;
+        o[1] = cy;
+        o[2] = cz;
+      }
+    }
+  }
+  cluster.sync();  // no CTA may exit while a peer can still store into its slots
+}
+
 // a8: out[b,c,j] = feat[b,c,idx[b,j]]
 __global__ void __launch_bounds__(256) gather_kernel(const float* __restrict__ feat, const int* __restrict__ idx,
                                                      int C, int N, int m, float* __restrict__ out) {
@@ -678,6 +826,45 @@ int launch_fps(const float* xyz, int stride, int B, int N, int m, int* idx, floa
   return check_launch();
 }
 
+template <int PPT, int WARPS, int CLUSTER>
+int launch_fps_direct(const float* xyz, int stride, int B, int N, int m, int* idx, float* out_xyz, cudaStream_t st) {
+  const int n_pad = (N + 3) & ~3;
+  const size_t slot_bytes = (size_t)2 * WARPS * CLUSTER * sizeof(unsigned long long);
+  auto kern = fps_direct_kernel<PPT, WARPS, CLUSTER>;
+  static PerDeviceOnce once;
+  if (once.needed()) {
+    V3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(slot_bytes + 3 * kFpsDirectMaxN * sizeof(float))));
+    if (CLUSTER > 8) V3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    once.done();
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(B * CLUSTER);
+  cfg.blockDim = dim3(WARPS * 32);
+  cfg.dynamicSmemBytes = slot_bytes + (size_t)3 * n_pad * sizeof(float);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CLUSTER;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  V3D_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, xyz, stride, N, n_pad, m, idx, out_xyz));
+  return check_launch();
+}
+
+template <int WARPS, int CLUSTER>
+int launch_fps_direct_n(const float* xyz, int stride, int B, int N, int m, int* idx, float* out_xyz, cudaStream_t st) {
+  const int ppt = ceil_div(N, WARPS * 32 * CLUSTER);
+  if (ppt <= 1) return launch_fps_direct<1, WARPS, CLUSTER>(xyz, stride, B, N, m, idx, out_xyz, st);
+  if (ppt <= 2) return launch_fps_direct<2, WARPS, CLUSTER>(xyz, stride, B, N, m, idx, out_xyz, st);
+  if (ppt <= 4) return launch_fps_direct<4, WARPS, CLUSTER>(xyz, stride, B, N, m, idx, out_xyz, st);
+  if (ppt <= 8) return launch_fps_direct<8, WARPS, CLUSTER>(xyz, stride, B, N, m, idx, out_xyz, st);
+  if (ppt <= 16) return launch_fps_direct<16, WARPS, CLUSTER>(xyz, stride, B, N, m, idx, out_xyz, st);
+  return V3D_ERR_INVALID_ARGUMENT;
+}
+
 }  // namespace
 }  // namespace v3d
 
@@ -694,6 +881,9 @@ static int fps_dispatch(const float* xyz, int stride, int B, int N, int m, int* 
   if (stride == 4 && (reinterpret_cast<uintptr_t>(xyz) & 15)) return V3D_ERR_INVALID_ARGUMENT;
   const int per_cta = ceil_div(N, kFpsCluster);
   const int ppt = ceil_div(per_cta, kFpsThreads);
+  // 4 warps x 8 CTAs: measured best of {16, 8, 4 warps} x {8, 16 CTAs} (profiles/r02_fps_sweep.json): fewer warps =
+  // fewer words to exchange and poll per step; 16-CTA clusters do not all fit on the chip at once for B = 8
+  if (N <= kFpsDirectMaxN) return launch_fps_direct_n<4, 8>(xyz, stride, B, N, m, idx, out_xyz, st);
   if (ppt <= 1) return launch_fps<1>(xyz, stride, B, N, m, idx, out_xyz, st);
   if (ppt <= 2) return launch_fps<2>(xyz, stride, B, N, m, idx, out_xyz, st);
   if (ppt <= 4) return launch_fps<4>(xyz, stride, B, N, m, idx, out_xyz, st);
