@@ -310,6 +310,14 @@ V3D_API int v3d_ball_query_msg_select(const void* sorted, const int* row_offsets
                                       const float* radii_host, const int* nsamples_host, int* const* idx_host,
                                       v3d_stream_t stream);
 
+/* BEVFeatureGatherer.forward (vision3d/detector/layers.py:30-50): bilinear grid_sample (align_corners, zero padding) of
+ * the BEV map at the keypoints, with the reference's index arithmetic (pixel = (xy - offset) / pixel_size, clamp,
+ * (size - 2) normaliser, x <-> W swap). map_nhwc (B, H, W, C) f32 = a channels_last (B, C, H, W) tensor, C % 4 == 0;
+ * keypoints (B, M, 3); out (B, c_total, M) f32, channels [c_off, c_off + C) written. */
+V3D_API int v3d_bev_gather(const float* map_nhwc, int B, int H, int W, int C, const float* keypoints, int M,
+                           float x_offset, float y_offset, float pixel_x, float pixel_y, float* out, int c_total,
+                           int c_off, v3d_stream_t stream);
+
 /* a10 QueryAndGroup(use_xyz=True) reading ROW-major sources: xyz (rows, xyz_stride), feat rows of C floats
  * `feat_stride` floats apart (C may be 0; feat may alias xyz, e.g. the intensity column of (x,y,z,i) points),
  * dense (row = b*N + idx) or ragged (row = row_offsets[b] + idx) -> out[B, 3+C, M, nsample]. Spares the

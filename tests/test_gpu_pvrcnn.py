@@ -273,3 +273,28 @@ def test_sa_fused_kernel_vs_torch_expression(cuda, C, widths, ns):
     err = float((out[:, 3:3 + n2] - want).abs().max() / want.abs().max())
     assert err <= 1e-4, err
     assert bool((out[:, :3] == -7.0).all()) and bool((out[:, 3 + n2:] == -7.0).all())   # only its channel slice is written
+
+
+@pytest.mark.gpu
+def test_bev_gather_vs_torch_expression(cuda):
+    """v3d_bev_gather == the reference's BEVFeatureGatherer expression (torch ops + F.grid_sample), including keypoints
+    outside the map (clamped), the (size - 2) normaliser and the x <-> W swap; partial keypoint tiles; C = 128 and 8."""
+    from vision3d_b200 import pvrcnn
+    cfg = pvrcnn.PVRCNNConfig()
+    g = torch.Generator().manual_seed(3)
+    px = (np.asarray(cfg.VOXEL_SIZE[:2], np.float32) * np.float32(cfg.STRIDES[-1])).tolist()
+    for (B, C, H, W, M) in [(2, 128, 200, 176, 2048), (3, 8, 37, 21, 70)]:
+        fmap = torch.randn((B, C, H, W), generator=g).to(cuda).contiguous(memory_format=torch.channels_last)
+        lo = torch.tensor([cfg.GRID_BOUNDS[0] - 3.0, cfg.GRID_BOUNDS[1] - 3.0, -3.0])
+        span = torch.tensor([W * px[0] + 6.0, H * px[1] + 6.0, 4.0])
+        kp = (torch.rand((B, M, 3), generator=g) * span + lo).to(cuda)
+        kp[0, 0, :2] = torch.tensor(cfg.GRID_BOUNDS[:2])                      # exactly on the first pixel
+        want = pvrcnn.bev_gather(cfg, fmap, kp)
+        got = ops.bev_gather(fmap, kp, cfg.GRID_BOUNDS[:2], px)
+        assert got.shape == want.shape
+        assert float((got - want).abs().max()) <= 2e-6 * float(want.abs().max()), float((got - want).abs().max())
+        out = torch.zeros((B, C + 5, M), device=cuda)
+        ops.bev_gather(fmap, kp, cfg.GRID_BOUNDS[:2], px, out=out, c_off=5)
+        assert torch.equal(out[:, 5:], got) and bool((out[:, :5] == 0).all())
+    with pytest.raises(ops.V3DError):
+        ops.bev_gather(torch.zeros((1, 8, 4, 4), device=cuda), torch.zeros((1, 4, 3), device=cuda), [0, 0], [1, 1])

@@ -70,6 +70,8 @@ SIGNATURES = {
     "v3d_ball_query_sort_workspace_bytes": (c_size_t, [c_int]),
     "v3d_ball_query_sort_x": (c_int, [P, c_int, P, c_int, c_int, c_int, c_float, c_float, P, P, P]),
     "v3d_ball_query_msg_select": (c_int, [P, P, P, c_int, P, c_int, c_int, c_int, c_int, P, P, P, P]),
+    "v3d_bev_gather": (c_int, [P, c_int, c_int, c_int, c_int, P, c_int, c_float, c_float, c_float, c_float, P, c_int,
+                               c_int, P]),
     "v3d_query_and_group_rows": (c_int, [P, c_int, P, c_int, c_int, c_int, P, P, P, c_int, c_int, c_int, P, P]),
     "v3d_sa_mlp_prepared_bytes": (c_size_t, [c_int, c_int]),
     "v3d_sa_mlp_prepare": (c_int, [P, c_int, c_int, P, c_size_t, P]),

@@ -820,6 +820,63 @@ __global__ void __launch_bounds__(256) pad_batch_kernel(const float* __restrict_
   }
 }
 
+// BEVFeatureGatherer.forward (detector/layers.py:30-50): bilinear F.grid_sample(align_corners=True, zero padding) of
+// the channels-last BEV map at the keypoints, index arithmetic restated op for op in fp32 (including the reference's
+// (size - 2) normaliser and its x <-> W swap) so that positions agree with the torch expression to the last bit or
+// two. A CTA handles 32 keypoints: a warp reads the four corner rows of a keypoint with 128-bit loads (lane = 4
+// channels), results are transposed through shared memory and written as 128-byte rows of the channel-major output.
+__global__ void __launch_bounds__(256) bev_gather_kernel(const float* __restrict__ map, int H, int W, int C,
+                                                         const float* __restrict__ kp, int M, float x_off, float y_off,
+                                                         float px, float py, float* __restrict__ out, int c_total,
+                                                         int c_off) {
+  __shared__ float tile[128][33];
+  const int b = blockIdx.y, m0 = blockIdx.x * 32, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int cb = 0; cb < C; cb += 128) {
+    for (int q = warp; q < 32; q += 8) {
+      const int m = m0 + q;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int c = cb + 4 * lane;
+      if (m < M && c < C) {
+        const float* k = kp + ((size_t)b * M + m) * 3;
+        // indices = (xy - pixel_offset) / (base_pixel * stride); clamp to [0, dims]; 2 * (i / (dims - 1)) - 1
+        float i0 = __fdiv_rn(__fsub_rn(__ldg(k), x_off), px);       // along x, clamped with W - 1
+        float i1 = __fdiv_rn(__fsub_rn(__ldg(k + 1), y_off), py);   // along y, clamped with H - 1
+        i0 = fminf(fmaxf(i0, 0.f), (float)(W - 1));
+        i1 = fminf(fmaxf(i1, 0.f), (float)(H - 1));
+        const float n0 = __fsub_rn(__fmul_rn(2.f, __fdiv_rn(i0, (float)(W - 2))), 1.f);
+        const float n1 = __fsub_rn(__fmul_rn(2.f, __fdiv_rn(i1, (float)(H - 2))), 1.f);
+        // after .flip(3): grid x = n1 (samples along W), grid y = n0 (samples along H)
+        const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(n1, 1.f), 2.f), (float)(W - 1));
+        const float iy = __fmul_rn(__fdiv_rn(__fadd_rn(n0, 1.f), 2.f), (float)(H - 1));
+        const float fx = floorf(ix), fy = floorf(iy);
+        const int x0 = (int)fx, y0 = (int)fy;
+        const float wx1 = __fsub_rn(ix, fx), wx0 = __fsub_rn(__fadd_rn(fx, 1.f), ix);
+        const float wy1 = __fsub_rn(iy, fy), wy0 = __fsub_rn(__fadd_rn(fy, 1.f), iy);
+        const float wgt[4] = {__fmul_rn(wx0, wy0), __fmul_rn(wx1, wy0), __fmul_rn(wx0, wy1), __fmul_rn(wx1, wy1)};
+#pragma unroll
+        for (int t = 0; t < 4; t++) {   // nw, ne, sw, se: the order torch accumulates in
+          const int x = x0 + (t & 1), y = y0 + (t >> 1);
+          if (x >= 0 && x < W && y >= 0 && y < H) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(map + (((size_t)b * H + y) * W + x) * C + c));
+            acc.x = fmaf(v.x, wgt[t], acc.x);
+            acc.y = fmaf(v.y, wgt[t], acc.y);
+            acc.z = fmaf(v.z, wgt[t], acc.z);
+            acc.w = fmaf(v.w, wgt[t], acc.w);
+          }
+        }
+      }
+      tile[4 * lane][q] = acc.x;
+      tile[4 * lane + 1][q] = acc.y;
+      tile[4 * lane + 2][q] = acc.z;
+      tile[4 * lane + 3][q] = acc.w;
+    }
+    __syncthreads();
+    for (int cc = warp; cc < 128; cc += 8)
+      if (cb + cc < C && m0 + lane < M) out[((size_t)b * c_total + c_off + cb + cc) * M + m0 + lane] = tile[cc][lane];
+    __syncthreads();
+  }
+}
+
 template <int PPT>
 int launch_fps(const float* xyz, int stride, int B, int N, int m, int* idx, float* out_xyz, cudaStream_t st) {
   fps_cluster_kernel<PPT><<<B * kFpsCluster, kFpsThreads, 0, st>>>(xyz, stride, N, m, idx, out_xyz);
@@ -1111,5 +1168,17 @@ extern "C" int v3d_ball_query_msg_select(const void* sorted, const int* row_offs
     default: V3D_BQS(4); break;
   }
 #undef V3D_BQS
+  return check_launch();
+}
+
+extern "C" int v3d_bev_gather(const float* map_nhwc, int B, int H, int W, int C, const float* keypoints, int M,
+                              float x_offset, float y_offset, float pixel_x, float pixel_y, float* out, int c_total,
+                              int c_off, v3d_stream_t stream) {
+  if (!map_nhwc || !keypoints || !out || B <= 0 || B > 65535 || H < 3 || W < 3 || C <= 0 || (C & 3) || M <= 0 ||
+      c_off < 0 || c_off + C > c_total || !(pixel_x > 0.f) || !(pixel_y > 0.f))
+    return V3D_ERR_INVALID_ARGUMENT;
+  if (reinterpret_cast<uintptr_t>(map_nhwc) & 15) return V3D_ERR_INVALID_ARGUMENT;
+  bev_gather_kernel<<<dim3(ceil_div(M, 32), B), 256, 0, as_stream(stream)>>>(map_nhwc, H, W, C, keypoints, M, x_offset,
+                                                                             y_offset, pixel_x, pixel_y, out, c_total, c_off);
   return check_launch();
 }

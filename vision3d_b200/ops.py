@@ -567,6 +567,24 @@ class BallQueryBounds:
         return self
 
 
+def bev_gather(feature_map, keypoints, xy_offset, pixel_size, out=None, c_off=0):
+    """BEVFeatureGatherer.forward (detector/layers.py:30-50). feature_map: (B, C, H, W) f32 in channels_last memory;
+    keypoints (B, M, 3); xy_offset = GRID_BOUNDS[:2]; pixel_size = float32(VOXEL_SIZE[:2]) * STRIDES[-1].
+    -> (B, C, M), or channels [c_off, c_off + C) of `out` (B, c_total, M)."""
+    B, C, H, W = feature_map.shape
+    if not feature_map.is_contiguous(memory_format=torch.channels_last) or feature_map.dtype != _F32 or not feature_map.is_cuda:
+        raise V3DError("bev_gather: feature_map must be a channels_last f32 CUDA tensor")
+    kp = _cuda_f32(keypoints, "keypoints", 3)
+    M = kp.shape[1]
+    if out is None:
+        out = torch.empty((B, C, M), dtype=_F32, device=kp.device)
+    with torch.cuda.device(kp.device):
+        check(_lib.load().v3d_bev_gather(feature_map.data_ptr(), B, H, W, C, kp.data_ptr(), M, float(xy_offset[0]),
+                                         float(xy_offset[1]), float(pixel_size[0]), float(pixel_size[1]), out.data_ptr(),
+                                         out.shape[1], int(c_off), _stream()), "v3d_bev_gather")
+    return out
+
+
 class BallQuerySorted:
     """x-bucketed copy of a source in random row order + its chunk boxes, for the selecting ball query
     (v3d_ball_query_sort_x / _bounds / _msg_select): `.build(xyz, row_offsets)` once per step, then

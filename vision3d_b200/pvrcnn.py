@@ -353,7 +353,8 @@ class KeypointStage:
             ops.to_global(e.indices[lv], e.n_rows[lv], self.level_vs[lv], self.level_off, out=self.level_xyz[lv])
 
     def _bev(self):
-        self.kp_features[:, 384:] = bev_gather(self.cfg, self.eng.bev_nhwc, self.keypoints)
+        ops.bev_gather(self.eng.bev_nhwc, self.keypoints, self.cfg.GRID_BOUNDS[:2], self._bev_pixel, out=self.kp_features,
+                       c_off=384)
 
     def _build_plan(self):
         chans = [sum(m[-1][0].shape[0] for m in sa) for sa in self.sa_mlps]      # 32, 32, 64, 128, 128
@@ -373,7 +374,8 @@ class KeypointStage:
                 else:
                     plan.append(("sa%d/group_r%d" % (i, r), (lambda i=i, r=r: self._sa_group(i, r))))
                     plan.append(("sa%d/mlp+max_r%d(torch)" % (i, r), (lambda i=i, r=r: self._sa_mlp(i, r))))
-        plan.append(("bev_gather(torch)", self._bev))
+        self._bev_pixel = (np.asarray(self.cfg.VOXEL_SIZE[:2], np.float32) * np.float32(self.cfg.STRIDES[-1])).tolist()
+        plan.append(("bev_gather", self._bev))
         plan.append(("roi/ball_query", self._roi_query))
         self._roi_out = [None] * len(self.cfg.SAMPLES_PN)
         if self.fused_sa:
