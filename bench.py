@@ -482,6 +482,10 @@ def c3_block(args, dev, hbm_peak):
             fl = 2 * rows_ * (dims[0] * dims[1] + dims[1] * dims[2])
             r.update(rows=rows_, mlp=dims, gflop=round(fl / 1e9, 2), tflops=round(fl / us / 1e6, 2),
                      grouped_bytes_not_materialised=4 * rows_ * dims[0])
+        elif name == "bev_gather":
+            C_bev = stage.eng.bev_nhwc.shape[1]
+            nb = B * M * (4 * C_bev * 4 + 12) + 4 * B * M * C_bev    # 4 corner rows + keypoint in, C floats out
+            r.update(alg_bytes=nb, gbs=round(nb / us / 1e3, 1), frac=round(nb / us / 1e3 / hbm_peak, 4))
         elif "/group_r" in name:
             ns = 16 if name.endswith("0") else 32
             if name.startswith("roi"):
@@ -517,7 +521,8 @@ def c3_block(args, dev, hbm_peak):
                     "h2d_bytes_per_step": h_pts.numel() * 4 + h_grid.numel() * 4, "d2h_bytes_per_step": h_out.numel() * 4},
             "ms_keypoint_ops_only": round(keypoint_only / 1e3, 3), "ms_sum_of_ops": round(total_us / 1e3, 3),
             "mlp": "shared MLPs fused with the grouping and the max (v3d_sa_fused: tcgen05 bf16x3, fp32 accumulate, "
-                   "parity-tested <= 1e-4); BEV gather and the 3072->256->256 reduction in torch (fp32, TF32 off)",
+                   "parity-tested <= 1e-4); BEV gather = v3d_bev_gather; the 3072->256->256 reduction MLP = two torch "
+                   "Linear layers (cuBLAS fp32, TF32 off)",
             "active_sites_per_level": rows, "per_op": table, "cpu_baseline": cpu}
 
 

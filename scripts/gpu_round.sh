@@ -47,12 +47,12 @@ if [[ " $WHAT " == *" ncu "* ]]; then
   timeout 400 ncu --set full --clock-control none -k 'regex:.*(vox_|table_|rule_|conv_mark|conv_scan|conv_rank|dense_|feature_pack|nms_|topk_rows|cls_logits|reg_gather|head_decode|pack_kernel).*' \
       --launch-skip 52 --launch-count 52 -o $OUT/${TAG}_prof_rest -f python scripts/ncu_step.py --steps 2 --rpn fused_nhwc \
       > $OUT/${TAG}_ncu_rest.log 2>&1
-  timeout 500 ncu --set full --clock-control none -k 'regex:.*(sa_fused|ball_query|fps_cluster|bq_bounds|query_group|sa_pack|to_global|batch_offsets).*' \
-      --launch-skip 31 --launch-count 31 -o $OUT/${TAG}_prof_c3 -f python scripts/ncu_c3.py 2 \
+  timeout 500 ncu --set full --clock-control none -k 'regex:.*(sa_fused|ball_query|fps_|bq_bounds|bs_|bev_gather|query_group|sa_pack|to_global|batch_offsets).*' \
+      --launch-skip 40 --launch-count 40 -o $OUT/${TAG}_prof_c3 -f python scripts/ncu_c3.py 2 \
       > $OUT/${TAG}_ncu_c3.log 2>&1
   # summarise on the box and leave the (large) reports behind: gpurun_out is limited to 64 MiB
   python scripts/summarize_ncu.py launches $OUT/${TAG}_launches.csv > $OUT/${TAG}_launches.md 2>&1
-  python scripts/summarize_ncu.py launches $OUT/${TAG}_c3_launches.csv fps_cluster > $OUT/${TAG}_c3_launches.md 2>&1
+  python scripts/summarize_ncu.py launches $OUT/${TAG}_c3_launches.csv fps_ > $OUT/${TAG}_c3_launches.md 2>&1
   python scripts/summarize_ncu.py counters $OUT/${TAG}_prof_conv.ncu-rep sparse_conv_tc > $OUT/${TAG}_conv_counters.md 2>&1
   python scripts/summarize_ncu.py counters $OUT/${TAG}_prof_c3.ncu-rep "" > $OUT/${TAG}_c3_counters.md 2>&1
   python scripts/summarize_ncu.py full $OUT/${TAG}_prof_rest.ncu-rep > $OUT/${TAG}_ncu_full.md 2>&1

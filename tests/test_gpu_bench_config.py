@@ -32,6 +32,7 @@ RPN_TF32_TOL = 1e-2   # of max|fmap|; cuDNN TF32 (10-bit mantissa operands, fp32
 def test_benchmarked_engine_stage_by_stage(cuda, workload, frames):
     eng, model, cfg = second.make_bench_engine(workload, frames, cuda)
     assert eng.graph is not None and eng.rpn_mode == "fused_nhwc" and eng.fused_head and eng.grouped_nms
+    assert eng.overlap_rulebooks   # rule-book chain on the second stream, as benchmarked
     B, n_cls, K = frames, cfg.NUM_CLASSES, cfg.TOPK
     clouds = synth.make_batch(0, B, second.PTS_PER_FRAME)   # bench.py's first batch of rank 0
     got = eng.infer(clouds)
@@ -208,3 +209,22 @@ def test_iou_many_rows_chunked_launch(cuda):
     sel = np.r_[0:64, M // 2:M // 2 + 64, 65535 * 16 - 8:M]
     want = oracle.box_iou_rotated(b1[sel], b2, 1)
     assert np.array_equal(got[sel].view(np.uint32), want.view(np.uint32))
+
+
+def test_rulebook_chain_on_second_stream_is_bit_identical(cuda):
+    """The captured step with the site-table / rule-book chain on its own stream (a parallel graph branch; the
+    convolutions wait per level) returns exactly what the single-stream step returns, replay after replay, on
+    alternating inputs (a missing dependency would show up as stale rule tables of the previous batch)."""
+    frames = 4
+    e1, _, _ = second.make_bench_engine("t16", frames, cuda, overlap_rulebooks=True)
+    e0, _, _ = second.make_bench_engine("t16", frames, cuda, overlap_rulebooks=False)
+    assert e1.graph is not None and e0.graph is not None
+    for seed in (0, 1, 0, 2, 1):
+        clouds = synth.make_batch(seed, frames, second.PTS_PER_FRAME)
+        a, b = e1.infer(clouds), e0.infer(clouds)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+        assert torch.equal(e1.result, e0.result)
+        for lv in range(5):
+            n = int(e0.n_rows[lv].item())
+            assert int(e1.n_rows[lv].item()) == n and torch.equal(e1.indices[lv][:n], e0.indices[lv][:n])

@@ -214,7 +214,7 @@ class KeypointStage:
                   self.pooled (B, n, 256); per-source ball-query indices in self.sa_idx for the parity tests."""
 
     def __init__(self, model: PVRCNNB200, batch_size, points_per_frame, n_proposals, device, level_caps=None,
-                 fused_sa=True):
+                 fused_sa=True, overlap_rulebooks=True):
         cfg = model.cfg
         self.cfg, self.B, self.N, self.n = cfg, int(batch_size), int(points_per_frame), int(n_proposals)
         self.dev = dev = torch.device(device)
@@ -222,7 +222,8 @@ class KeypointStage:
         B, M = self.B, cfg.NUM_KEYPOINTS
         # sparse backbone: the SecondEngine plan up to the dense BEV, every level's fp32 rows kept
         self.eng = second.SecondEngine(model, B, B * self.N, dev, level_caps=level_caps, use_graph=False,
-                                       rpn_mode="none", keep_level_features=True)
+                                       rpn_mode="none", keep_level_features=True,
+                                       overlap_rulebooks=overlap_rulebooks)
         self.points = torch.zeros((B, self.N, 4), dtype=torch.float32, device=dev)
         self.eng.points = self.points.view(B * self.N, 4)      # the voxelizer reads the same buffer
         self.eng.frame_off.copy_(torch.arange(B + 1, dtype=torch.int32) * self.N)
@@ -398,6 +399,9 @@ class KeypointStage:
 
     def step(self):
         with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            if self.eng.overlap_rulebooks:   # rule-book chain of the backbone on the engine's second stream
+                self.eng.run_overlapped([(name[9:] if name.startswith("backbone/") else name, fn) for name, fn in self.plan])
+                return self.pooled
             for _, fn in self.plan:
                 fn()
         return self.pooled

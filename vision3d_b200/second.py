@@ -305,7 +305,8 @@ BENCH_WORKLOADS = {
     # BASELINE config 5: 3-class defaults (core/config.py), global batch 64 sharded over the ranks (strong scaling)
     "c5": dict(cfg="three", frames_per_gpu=None, global_batch=64),
 }
-BENCH_ENGINE_FLAGS = dict(use_graph=True, tensor_cores=True, rpn_mode="fused_nhwc", fused_head=True, grouped_nms=True)
+BENCH_ENGINE_FLAGS = dict(use_graph=True, tensor_cores=True, rpn_mode="fused_nhwc", fused_head=True, grouped_nms=True,
+                          overlap_rulebooks=True)
 
 
 def make_bench_engine(workload, frames, device, seed=0, **overrides):
@@ -334,13 +335,17 @@ def _fold_bn(bn):
 class SecondEngine:
     def __init__(self, model: SecondB200, batch_size: int, points_capacity: int, device, level_caps=None,
                  use_graph=True, cap_policy=0, frame_points_capacity=None, tensor_cores=True, rpn_mode="fused",
-                 fused_head=True, grouped_nms=True, keep_level_features=False, result_out=None, post_step=None):
+                 fused_head=True, grouped_nms=True, keep_level_features=False, result_out=None, post_step=None,
+                 overlap_rulebooks=False):
         """rpn_mode: "module" | "fused" | "fused_nhwc" (SECOND, detector/second.py:49-94) or "none" (PV_RCNN feeds the
         BEV map straight to the proposal layer, detector/model.py:79-80). keep_level_features: the strided convs
         entering levels 1-3 also write fp32 rows (PV_RCNN's cnn returns every level, sparse_cnn.py:135-146).
         result_out: external (N+1, 11) f32 buffer the packed detections are written to (multi-GPU: this rank's slot
         of the all-gather buffer, so the collective runs in place); post_step: callable issued at the end of every
-        step, INSIDE the captured graph (the all-gather of SURVEY 8e)."""
+        step, INSIDE the captured graph (the all-gather of SURVEY 8e). overlap_rulebooks: the site table and the rule
+        books of ALL levels depend on voxel coordinates only, never on features -- they run as one chain on a second
+        stream (a parallel branch of the captured graph), and a convolution waits only for the rule book of its own
+        level: the latency-bound index kernels of level L+1.. execute under the tensor-core kernels of level L."""
         cfg = model.cfg
         self.grouped_nms = bool(grouped_nms)
         self.keep_level_features = bool(keep_level_features)
@@ -348,6 +353,8 @@ class SecondEngine:
         self.dev = torch.device(device)
         self.model = model.to(self.dev).eval()
         self.use_graph = use_graph
+        self.overlap_rulebooks = bool(overlap_rulebooks)
+        self._rb_stream = torch.cuda.Stream(device=self.dev) if self.overlap_rulebooks else None
         B, dev = self.B, self.dev
         caps = list(level_caps or DEFAULT_LEVEL_CAPS)
         caps[0] = cfg.MAX_VOXELS
@@ -649,9 +656,45 @@ class SecondEngine:
         for lv in range(5):
             r[self.N, 1 + lv] = self.n_rows[lv].float()[0]
 
-    def _step(self):
-        for _, _, fn in self.plan:
+    @staticmethod
+    def _rulebook_needed_by(name):
+        """Rule-book op a plan entry has to wait for (None: none)."""
+        if name.startswith("subm_L"):
+            return "rulebook_subm_L" + name[6]
+        if name.startswith("sconv_L"):
+            return "rulebook_conv_L" + name[7]
+        return None
+
+    def run_overlapped(self, entries):
+        """Issue [(name, fn)] in order, the site-table / rule-book entries on the second stream (see __init__)."""
+        main, side = torch.cuda.current_stream(self.dev), self._rb_stream
+        done, waited, last = {}, set(), None
+        for name, fn in entries:
+            if name.startswith(("site_table", "rulebook_")):
+                if last is None:        # the chain starts when the voxel coordinates exist
+                    side.wait_event(main.record_event())
+                with torch.cuda.stream(side):
+                    fn()
+                    done[name] = side.record_event()
+                last = name
+                continue
+            need = self._rulebook_needed_by(name)
+            if need is not None and need not in waited:
+                main.wait_event(done[need])
+                waited.add(need)
+            if name == "dense" and last is not None and last not in waited:   # join: the chain never outlives the step
+                main.wait_event(done[last])
+                waited.add(last)
             fn()
+        if last is not None and last not in waited:
+            main.wait_event(done[last])
+
+    def _step(self):
+        if self.overlap_rulebooks:
+            self.run_overlapped([(name, fn) for name, _, fn in self.plan])
+        else:
+            for _, _, fn in self.plan:
+                fn()
 
     def profile_ops(self, iters=5):
         """Average device time (us) of every op of the plan, measured eagerly with CUDA events on the
