@@ -1,5 +1,5 @@
 """Per-op device time of the sparse-conv layers of the t16 workload for the current V3D_TC_* environment
-(one process per setting: the knobs are read once). Usage: V3D_TC_VARIANT=4 python scripts/conv_variant.py"""
+(one process per setting: the knobs are read once). Usage: V3D_TC_FETCH=2 python scripts/conv_variant.py"""
 import os
 import sys
 
@@ -16,5 +16,5 @@ eng.step_e2e()
 torch.cuda.synchronize()
 ops_t = eng.profile_ops(iters=5)
 conv = [(n, round(t)) for n, t in ops_t if n.startswith(("subm_L", "sconv_L"))]
-print("VARIANT=%s SKIP=%s conv total %.0f us :" % (os.environ.get("V3D_TC_VARIANT"), os.environ.get("V3D_TC_SKIP_ABSENT"),
-                                                   sum(t for _, t in conv)), conv, flush=True)
+print("V3D_TC_FETCH=%s conv total %.0f us :" % (os.environ.get("V3D_TC_FETCH"), sum(t for _, t in conv)), conv,
+      flush=True)

@@ -64,6 +64,29 @@ __device__ __forceinline__ uint32_t group_mask(uint32_t m) {
   return g;
 }
 
+// One 16-byte piece of a gathered row: dst + kDstOff <- base[idx * kRowBytes], zeros if idx < 0. Written as one PTX
+// block so that the row costs exactly three SASS instructions (ISETP, IMAD.WIDE, LDGSTS with the zero-fill
+// predicate); a predicated-off copy does not read its source address.
+template <int kRowBytes, int kDstOff, bool kBypassL1>
+__device__ __forceinline__ void gather_row16(uint32_t dst, const unsigned char* base, int idx) {
+  if (kBypassL1)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 a;\n\t"
+        "setp.lt.s32 p, %2, 0;\n\t"
+        "mad.wide.s32 a, %2, %3, %1;\n\t"
+        "cp.async.cg.shared.global [%0+%4], [a], 16, p;\n\t}" ::"r"(dst),
+        "l"(base), "r"(idx), "n"(kRowBytes), "n"(kDstOff)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 a;\n\t"
+        "setp.lt.s32 p, %2, 0;\n\t"
+        "mad.wide.s32 a, %2, %3, %1;\n\t"
+        "cp.async.ca.shared.global [%0+%4], [a], 16, p;\n\t}" ::"r"(dst),
+        "l"(base), "r"(idx), "n"(kRowBytes), "n"(kDstOff)
+        : "memory");
+}
+
 constexpr int pow2_cols(int c) { return c <= 32 ? 32 : (c <= 64 ? 64 : (c <= 128 ? 128 : (c <= 256 ? 256 : 512))); }
 
 template <int CIN, int COUT>
@@ -92,8 +115,11 @@ struct SlotMeta {
   int end;   // 1 = all tiles done
 };
 
-template <int CIN, int COUT, int kFetchWarps>
-__global__ void __launch_bounds__(32 * (kWarpFetch0 + kFetchWarps), 1)
+// kVer selects the fetch scheme: 1 = "lean" (round 2), 2 = "phase-aligned" (below: 4 instructions per copied row
+// instead of 9, weight stream on its own warp), 3 = 2 with L1-bypassing copies (cp.async.cg). All produce
+// bit-identical results; V3D_TC_FETCH=1|2|3 picks one.
+template <int CIN, int COUT, int kFetchWarps, int kVer>
+__global__ void __launch_bounds__(32 * (kWarpFetch0 + kFetchWarps + (kVer >= 2 ? 1 : 0)), 1)
 sparse_conv_tc_kernel(const unsigned char* __restrict__ feat, const unsigned char* __restrict__ wprep,
                       const int* __restrict__ nbr, int nbr_stride, const int* __restrict__ n_out_ptr, int out_cap,
                       int KV, const float* __restrict__ scale, const float* __restrict__ shift, int relu,
@@ -113,6 +139,7 @@ sparse_conv_tc_kernel(const unsigned char* __restrict__ feat, const unsigned cha
   SlotMeta* meta = reinterpret_cast<SlotMeta*>(acc_empty + 2);  // [8] fetcher -> MMA issuer (per stage)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(meta + 8);
   uint32_t* fmask = tmem_slot + 1;  // [2] offsets used by the tile being staged (parity double buffer)
+  int* neg_row = reinterpret_cast<int*>(tail + 512);  // [128] all -1 (scheme 2: rule row of a non-existent offset)
   float* s_scale = reinterpret_cast<float*>(tail + 1024);
   float* s_shift = s_scale + COUT;
 
@@ -132,6 +159,7 @@ sparse_conv_tc_kernel(const unsigned char* __restrict__ feat, const unsigned cha
     fmask[0] = fmask[1] = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (tid < kTileM) neg_row[tid] = -1;
   for (int c = tid; c < COUT; c += (int)blockDim.x) {
     s_scale[c] = scale ? __ldg(&scale[c]) : 1.0f;
     s_shift[c] = shift ? __ldg(&shift[c]) : 0.0f;
@@ -244,8 +272,8 @@ sparse_conv_tc_kernel(const unsigned char* __restrict__ feat, const unsigned cha
       }
       it++;
     }
-  } else {
-    // =========================== fetchers ===========================
+  } else if (kVer == 1) {
+    // =========================== fetchers (scheme 1) ===========================
     // What bounds this loop was measured on B200 by switching its parts off one at a time and by trying five
     // alternative fetch schemes (profiles/r02_conv_fetch_bisect.md): with no MMAs, no gather copies and no weight
     // stream the control skeleton alone still runs at ~700 clk per K=64 slot (full kernel ~900, the MMAs 444);
@@ -341,6 +369,130 @@ sparse_conv_tc_kernel(const unsigned char* __restrict__ feat, const unsigned cha
       }
       mbar_arrive(&full[s]);
     }
+  } else if (warp < kWarpFetch0 + kFetchWarps) {
+    // =========================== fetchers (scheme 2: phase-aligned rows) ===========================
+    // Scheme 1 spends ~140 SASS instructions per slot in every fetch warp, 72 of them in the eight row copies
+    // (compare, 64-bit multiply, two selects, lane-offset OR, 64-bit add, destination add, LDGSTS), and the measured
+    // cost of that dependent chain is ~5 clk per instruction (profiles/r02_conv_fetch_bisect.md). Here a lane copies
+    // the eight tile rows r_j = 64 h + 8 j + p that share ONE swizzle phase p (= r & 7): the destination of row j is
+    // a constant register + j * 1024 (an LDGSTS immediate), the source is one IMAD.WIDE (index * row bytes + lane
+    // base), and an absent neighbour is the LDGSTS zero-fill predicate on the raw index (no address select: a
+    // predicated-off copy does not read its source, the CUTLASS zfill convention). Rule tile rows are staged
+    // permuted -- entry of tile row r at ((r & 7) * 2 + (r >> 6)) * 8 + ((r >> 3) & 7) -- so that the lane's eight
+    // entries are still two 128-bit shared loads. The weight image / slot meta / expect_tx arrival moved to a warp
+    // of their own (below), off the critical chain of fetch warp 0.
+    constexpr int NF = kFetchWarps * 32;
+    static_assert(kFetchWarps == 8, "one swizzle phase per fetch warp");
+    constexpr int kRowBytes = 4 * CIN;
+    const int fw = warp - kWarpFetch0, gt = fw * 32 + lane;
+    const int half = lane >> 4, part = (lane >> 3) & 1, unit = lane & 7;
+    const int off = (unit * 8) / CIN;
+    const int src_byte = part * (2 * CIN) + ((unit * 8) % CIN) * 2;
+    const uint32_t ring_u32 = smem_u32(ring);
+    const uint32_t dst_lane =
+        ring_u32 + (uint32_t)(part * kATileBytes + (64 * half + fw) * 128 + ((unit ^ fw) << 4));
+    const unsigned char* feat_lane = feat + src_byte;
+    const int idx_pos = (fw * 2 + half) * 8;  // first of this lane's 8 consecutive (permuted) rule entries
+
+    constexpr int kParts = NF / kTileM, kPre = (kMaxKV + kParts - 1) / kParts;
+    const int srow = gt & (kTileM - 1), kpart = gt >> 7;
+    const int spos = ((srow & 7) * 2 + (srow >> 6)) * 8 + ((srow >> 3) & 7);
+    int pre[kPre];
+    auto prefetch = [&](int tile) {
+      const int o = tile * kTileM + srow;
+      const bool ok = tile < n_tiles && o < n_out;
+#pragma unroll
+      for (int j = 0; j < kPre; j++) {
+        const int k = kpart + kParts * j;
+        pre[j] = (ok && k < KV) ? __ldg(nbr + (size_t)k * nbr_stride + o) : -1;
+      }
+    };
+    prefetch(blockIdx.x);
+    uint32_t q = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+      asm volatile("bar.sync 1, %0;" ::"n"(NF + 32) : "memory");  // all copies that read idx_tile are issued
+      if (gt == 0) fmask[(it + 1) & 1] = 0u;
+      uint32_t mine = 0;
+#pragma unroll
+      for (int j = 0; j < kPre; j++) {
+        const int k = kpart + kParts * j;
+        if (k < KV) idx_tile[k * kTileM + spos] = pre[j];
+        if (__any_sync(0xffffffffu, pre[j] >= 0)) mine |= 1u << k;
+      }
+      if (lane == 0 && mine) atomicOr(&fmask[it & 1], mine);
+      asm volatile("bar.sync 1, %0;" ::"n"(NF + 32) : "memory");
+      uint32_t mask = fmask[it & 1];
+      if (mask == 0) mask = 1u;
+      mask = group_mask<C::kGK>(mask);
+      prefetch(tile + gridDim.x);
+      while (mask) {
+        const int g = __ffs(mask) - 1;
+        mask &= mask - 1;
+        // rule entries first: their shared-memory latency overlaps the wait for the stage
+        const int kk = g * C::kGK + off;
+        // a padded (non-existent) offset of the last group reads the all -1 row
+        const int4* idx_row = reinterpret_cast<const int4*>((kk < KV ? idx_tile + kk * kTileM : neg_row) + idx_pos);
+        const int4 sa = idx_row[0], sb = idx_row[1];
+        const uint32_t s = q % C::kStages;
+        mbar_wait(&empty[s], ((q / C::kStages) & 1u) ^ 1u);
+        const uint32_t dst = dst_lane + s * (uint32_t)C::kStageBytes;
+        gather_row16<kRowBytes, 0 * 1024, kVer == 3>(dst, feat_lane, sa.x);
+        gather_row16<kRowBytes, 1 * 1024, kVer == 3>(dst, feat_lane, sa.y);
+        gather_row16<kRowBytes, 2 * 1024, kVer == 3>(dst, feat_lane, sa.z);
+        gather_row16<kRowBytes, 3 * 1024, kVer == 3>(dst, feat_lane, sa.w);
+        gather_row16<kRowBytes, 4 * 1024, kVer == 3>(dst, feat_lane, sb.x);
+        gather_row16<kRowBytes, 5 * 1024, kVer == 3>(dst, feat_lane, sb.y);
+        gather_row16<kRowBytes, 6 * 1024, kVer == 3>(dst, feat_lane, sb.z);
+        gather_row16<kRowBytes, 7 * 1024, kVer == 3>(dst, feat_lane, sb.w);
+        cp_async_arrive_noinc(&full[s]);
+        q++;
+      }
+    }
+    {  // termination slot: the fetchers' share of the arrivals
+      const uint32_t s = q % C::kStages;
+      mbar_wait(&empty[s], ((q / C::kStages) & 1u) ^ 1u);
+      mbar_arrive(&full[s]);
+    }
+  } else {
+    // =========================== weight streamer (scheme 2) ===========================
+    // Walks the same slot sequence as the fetchers (same barriers, same usage mask) and per slot publishes the
+    // slot meta, posts the expect_tx arrival and launches the 1-D TMA bulk copy of the slot's weight image.
+    constexpr int NF = kFetchWarps * 32;
+    const uint32_t ring_u32 = smem_u32(ring);
+    uint32_t q = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+      asm volatile("bar.sync 1, %0;" ::"n"(NF + 32) : "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(NF + 32) : "memory");
+      uint32_t mask = fmask[it & 1];
+      if (mask == 0) mask = 1u;
+      mask = group_mask<C::kGK>(mask);
+      while (mask) {
+        const int g = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const uint32_t s = q % C::kStages;
+        mbar_wait(&empty[s], ((q / C::kStages) & 1u) ^ 1u);
+        if (lane == 0) {
+          meta[s].last = (mask == 0);
+          meta[s].end = 0;
+          mbar_arrive_expect_tx(&full[s], (uint32_t)C::kBBytes);
+          bulk_g2s(ring_u32 + s * (uint32_t)C::kStageBytes + kABytes, wprep + (size_t)g * C::kBBytes,
+                   (uint32_t)C::kBBytes, &full[s]);
+        }
+        __syncwarp();
+        q++;
+      }
+    }
+    {  // termination slot
+      const uint32_t s = q % C::kStages;
+      mbar_wait(&empty[s], ((q / C::kStages) & 1u) ^ 1u);
+      if (lane == 0) {
+        meta[s].last = 1;
+        meta[s].end = 1;
+        mbar_arrive(&full[s]);  // stands in for the expect_tx arrival of a real slot
+      }
+    }
   }
 
   tc_fence_before();
@@ -401,22 +553,49 @@ __global__ void feature_pack_kernel(const float* __restrict__ feat, const int* _
   }
 }
 
-template <int CIN, int COUT>
-int launch_tc(const unsigned char* feat, const unsigned char* wprep, const int* nbr, int nbr_stride, const int* n_out,
-              int out_cap, int KV, const float* scale, const float* shift, int relu, float* out,
-              unsigned char* out_packed, cudaStream_t st) {
+// Fetch scheme of the tensor-core kernel: V3D_TC_FETCH=1 "lean" (round 2), 2 phase-aligned, 3 = 2 + cp.async.cg.
+constexpr int kDefaultFetchScheme = 1;
+inline int tc_fetch_scheme() {
+  static const int v = [] {
+    const char* e = getenv("V3D_TC_FETCH");
+    if (e && e[0] == '1') return 1;
+    if (e && e[0] == '2') return 2;
+    if (e && e[0] == '3') return 3;
+    return kDefaultFetchScheme;
+  }();
+  return v;
+}
+
+template <int CIN, int COUT, int kVer>
+int launch_tc_ver(const unsigned char* feat, const unsigned char* wprep, const int* nbr, int nbr_stride, const int* n_out,
+                  int out_cap, int KV, const float* scale, const float* shift, int relu, float* out,
+                  unsigned char* out_packed, cudaStream_t st) {
   using C = TcCfg<CIN, COUT>;
   static PerDeviceOnce attr_once;
   if (attr_once.needed()) {
-    V3D_CUDA_TRY(cudaFuncSetAttribute(sparse_conv_tc_kernel<CIN, COUT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)C::kSmemBytes));
+    V3D_CUDA_TRY(cudaFuncSetAttribute(sparse_conv_tc_kernel<CIN, COUT, 8, kVer>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes));
     attr_once.done();
   }
   const int tiles_cap = ceil_div(out_cap, kTileM);
   const int grid = tiles_cap < kNumSMs ? (tiles_cap > 0 ? tiles_cap : 1) : kNumSMs;
-  sparse_conv_tc_kernel<CIN, COUT, 8><<<grid, 32 * (kWarpFetch0 + 8), C::kSmemBytes, st>>>(
+  sparse_conv_tc_kernel<CIN, COUT, 8, kVer><<<grid, 32 * (kWarpFetch0 + 8 + (kVer >= 2 ? 1 : 0)), C::kSmemBytes, st>>>(
       feat, wprep, nbr, nbr_stride, n_out, out_cap, KV, scale, shift, relu, out, out_packed);
   return check_launch();
+}
+
+template <int CIN, int COUT>
+int launch_tc(const unsigned char* feat, const unsigned char* wprep, const int* nbr, int nbr_stride, const int* n_out,
+              int out_cap, int KV, const float* scale, const float* shift, int relu, float* out,
+              unsigned char* out_packed, cudaStream_t st) {
+  if (tc_fetch_scheme() == 1)
+    return launch_tc_ver<CIN, COUT, 1>(feat, wprep, nbr, nbr_stride, n_out, out_cap, KV, scale, shift, relu, out,
+                                       out_packed, st);
+  if (tc_fetch_scheme() == 3)
+    return launch_tc_ver<CIN, COUT, 3>(feat, wprep, nbr, nbr_stride, n_out, out_cap, KV, scale, shift, relu, out,
+                                       out_packed, st);
+  return launch_tc_ver<CIN, COUT, 2>(feat, wprep, nbr, nbr_stride, n_out, out_cap, KV, scale, shift, relu, out,
+                                     out_packed, st);
 }
 
 inline bool tc_supported(int KV, int Cin, int Cout) {
