@@ -1,0 +1,104 @@
+#!/usr/bin/env bash
+# One time-boxed GPU pass for a small remaining budget (most important first; everything lands in gpurun_out/):
+#   1. parity of the phase-aligned conv fetch scheme (V3D_TC_FETCH=2): conv / voxelize kernel tests + the
+#      stage-by-stage test of the benchmarked engines
+#   2. per-layer conv times of schemes 1, 2, 3 on the same box (scripts/conv_variant.py)
+#   3. pick the fastest scheme that passed -> V3D_TC_FETCH for everything below
+#   4. bench.py (t16 + c5 + c3 + cpu baseline)
+#   5. ncu launch list of one eager step, ncu --set full counters of the conv launches
+#   6. the rest of the gpu test suite
+# usage: gpurun --timeout 640 -- 'bash scripts/gpu_final.sh r02y'
+set -u
+TAG=${1:-rXX}
+OUT=gpurun_out
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/${TAG}_gpu.txt 2>&1
+T0=$(date +%s)
+el() { echo "[$(( $(date +%s) - T0 )) s] $*"; }
+
+# ---- 1. parity of scheme 2
+V3D_TC_FETCH=2 timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_bench_config.py -m gpu -q -rf \
+    -p no:cacheprovider --timeout 240 \
+    -k "(sparse_conv or voxelize or stage_by_stage or second_stream) and not subprocess" \
+    > $OUT/${TAG}_tests_fetch2.log 2>&1
+RCP=$?
+el "scheme-2 run rc=$RCP: $(tail -1 $OUT/${TAG}_tests_fetch2.log)"
+grep -E "^FAILED|^ERROR|^E  " $OUT/${TAG}_tests_fetch2.log | head -10
+# scheme 2 is acceptable iff the run finished (no timeout / crash) and no conv / engine test failed
+RC2=0
+if [[ $RCP -ne 0 && $RCP -ne 1 ]]; then RC2=1; fi
+if ! grep -qE "passed" $OUT/${TAG}_tests_fetch2.log; then RC2=1; fi
+if grep -E "^FAILED|^ERROR" $OUT/${TAG}_tests_fetch2.log | grep -qE "sparse_conv|stage_by_stage|second_stream"; then RC2=1; fi
+el "scheme-2 parity verdict RC2=$RC2"
+
+# ---- 2. A/B/C of the fetch schemes
+for v in 2 3 1; do
+  V3D_TC_FETCH=$v timeout 120 python scripts/conv_variant.py > $OUT/${TAG}_conv_fetch$v.txt 2>&1
+  el "$(grep -h 'conv total' $OUT/${TAG}_conv_fetch$v.txt | cut -c1-400)"
+done
+
+# ---- 3. choose
+BEST=$(python - <<PY
+import re
+best, bt = 1, None
+tot = {}
+for v in (1, 2, 3):
+    try:
+        m = re.search(r"conv total (\d+)", open("$OUT/${TAG}_conv_fetch%d.txt" % v).read())
+        tot[v] = int(m.group(1))
+    except Exception:
+        pass
+ok2 = ($RC2 == 0)
+cands = [v for v in tot if v == 1 or ok2]
+best = min(cands, key=lambda v: tot[v]) if cands else 1
+print(best)
+PY
+)
+el "chosen fetch scheme: $BEST"
+echo "$BEST" > $OUT/${TAG}_chosen_scheme.txt
+export V3D_TC_FETCH=$BEST
+if [[ "$BEST" == "3" ]]; then
+  timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -p no:cacheprovider --timeout 150 -k "sparse_conv_tc" \
+      > $OUT/${TAG}_tests_fetch3.log 2>&1
+  el "scheme-3 parity rc=$?: $(tail -1 $OUT/${TAG}_tests_fetch3.log)"
+fi
+
+# ---- 4. bench
+timeout 420 python bench.py > $OUT/${TAG}_bench_N1.json 2> $OUT/${TAG}_bench.err
+el "bench rc=$?"
+tail -2 $OUT/${TAG}_bench.err
+python - <<PY
+import json
+try:
+    d = json.loads(open("$OUT/${TAG}_bench_N1.json").read().strip().splitlines()[-1])
+    print("bench:", d["value"], d["e2e"]["value"], d["ms_per_step"], d["roofline"]["frac"], d["clocks"])
+    print([(r["op"][:18], round(r["us"])) for r in d["per_op"]])
+    w = d["workloads"]
+    print("c5:", w["c5"] and (w["c5"]["value"], w["c5"]["ms_per_step"]))
+    c3 = w["c3"]
+    print("c3:", c3 and (c3.get("error") or (c3["value"], c3["ms_per_step"], [(r["op"][:14], round(r["us"])) for r in c3["per_op"] if not r["op"].startswith("backbone")])))
+except Exception as e:
+    print("bench parse failed", e)
+PY
+
+# ---- 5. ncu evidence for the chosen scheme
+timeout 150 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/${TAG}_launches.csv \
+    python scripts/ncu_step.py --steps 2 --rpn fused_nhwc > $OUT/${TAG}_ncu_list.log 2>&1
+python scripts/summarize_ncu.py launches $OUT/${TAG}_launches.csv > $OUT/${TAG}_launches.md 2>&1
+el "launch list done"
+timeout 300 ncu --set full --import-source on --clock-control none -k 'regex:.*(sparse_conv_tc).*' \
+    --launch-skip 14 --launch-count 10 -o $OUT/${TAG}_prof_conv -f python scripts/ncu_step.py --steps 2 --rpn fused_nhwc \
+    > $OUT/${TAG}_ncu_conv.log 2>&1
+python scripts/summarize_ncu.py counters $OUT/${TAG}_prof_conv.ncu-rep sparse_conv_tc > $OUT/${TAG}_conv_counters.md 2>&1
+python scripts/summarize_ncu.py traffic $OUT/${TAG}_prof_conv.ncu-rep "profiles/${TAG}_conv_counters.md (ncu --set full, one eager step, batch 16)" > $OUT/${TAG}_traffic_conv.json 2>&1
+rm -f $OUT/*.ncu-rep
+el "conv counters done"
+head -12 $OUT/${TAG}_conv_counters.md
+
+# ---- 6. everything else of the gpu suite (whatever time is left)
+timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider --timeout 300 \
+    --deselect tests/test_gpu_parity.py::test_voxelize_cluster_dsmem_variant_subprocess \
+    > $OUT/${TAG}_tests_all.log 2>&1
+el "full suite rc=$?: $(tail -1 $OUT/${TAG}_tests_all.log)"
+grep -E "^FAILED|^ERROR" $OUT/${TAG}_tests_all.log | head -20
+du -sh $OUT

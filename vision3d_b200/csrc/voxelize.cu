@@ -95,6 +95,8 @@ __device__ __forceinline__ bool point_cell(const float* __restrict__ pt, const V
   return true;
 }
 
+// kVec4: 4-channel points on a 16-byte aligned base are read with ONE 128-bit load per point (x, y, z, intensity)
+template <bool kVec4>
 __global__ void __launch_bounds__(kChunk) vox_insert_kernel(const float* __restrict__ points,
                                                             const int* __restrict__ frame_off,
                                                             VoxParams P, VoxWs W) {
@@ -107,9 +109,16 @@ __global__ void __launch_bounds__(kChunk) vox_insert_kernel(const float* __restr
   const unsigned int epoch = epoch24(calls);
   int c[3];
   float pt[3];
-  pt[0] = points[g * P.C + 0];
-  pt[1] = points[g * P.C + 1];
-  pt[2] = points[g * P.C + 2];
+  if (kVec4) {
+    const float4 p4 = __ldg(reinterpret_cast<const float4*>(points) + g);
+    pt[0] = p4.x;
+    pt[1] = p4.y;
+    pt[2] = p4.z;
+  } else {
+    pt[0] = points[g * P.C + 0];
+    pt[1] = points[g * P.C + 1];
+    pt[2] = points[g * P.C + 2];
+  }
   if (!point_cell(pt, P, c)) {
     W.pt_slot[g] = 0xFFFFFFFFu;
     return;
@@ -608,10 +617,15 @@ extern "C" int v3d_voxelize_batch(const float* points, int total_points, int max
     return check_launch();
   }
   dim3 grid(ceil_div(max_frame_points > 0 ? max_frame_points : 1, kChunk), B);
-  vox_insert_kernel<<<grid, kChunk, 0, st>>>(points, frame_offsets, P, W);
+  // 128-bit point loads / voxel-slot stores need 16-byte aligned bases (always true for whole torch allocations)
+  const bool vec4 = C == 4 && ((reinterpret_cast<uintptr_t>(points) | reinterpret_cast<uintptr_t>(voxels)) & 15) == 0;
+  if (vec4)
+    vox_insert_kernel<true><<<grid, kChunk, 0, st>>>(points, frame_offsets, P, W);
+  else
+    vox_insert_kernel<false><<<grid, kChunk, 0, st>>>(points, frame_offsets, P, W);
   vox_count_kernel<<<grid, kChunk, 0, st>>>(frame_offsets, W);
   vox_assign_kernel<<<grid, kChunk, 0, st>>>(points, frame_offsets, P, W, coords, voxel_offsets);
-  if (C == 4)
+  if (vec4)
     vox_scatter_kernel<true><<<grid, kChunk, 0, st>>>(points, frame_offsets, P, W, voxels, num_points,
                                                       max_pts <= 8 ? mean : nullptr);
   else
