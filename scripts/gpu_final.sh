@@ -17,7 +17,7 @@ T0=$(date +%s)
 el() { echo "[$(( $(date +%s) - T0 )) s] $*"; }
 
 # ---- 1. parity of scheme 2
-V3D_TC_FETCH=2 timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_bench_config.py -m gpu -q -rf \
+V3D_TC_FETCH=2 timeout 270 python -m pytest tests/test_gpu_parity.py tests/test_gpu_bench_config.py -m gpu -q -rf \
     -p no:cacheprovider --timeout 240 \
     -k "(sparse_conv or voxelize or stage_by_stage or second_stream) and not subprocess" \
     > $OUT/${TAG}_tests_fetch2.log 2>&1
@@ -32,8 +32,10 @@ if grep -E "^FAILED|^ERROR" $OUT/${TAG}_tests_fetch2.log | grep -qE "sparse_conv
 el "scheme-2 parity verdict RC2=$RC2"
 
 # ---- 2. A/B/C of the fetch schemes
-for v in 2 3 1; do
-  V3D_TC_FETCH=$v timeout 120 python scripts/conv_variant.py > $OUT/${TAG}_conv_fetch$v.txt 2>&1
+SCHEMES="2 3 1"
+if [[ $RC2 -ne 0 ]]; then SCHEMES="1"; fi   # a failed / hung scheme 2 is not timed (nor scheme 3, the same loop)
+for v in $SCHEMES; do
+  V3D_TC_FETCH=$v timeout 100 python scripts/conv_variant.py > $OUT/${TAG}_conv_fetch$v.txt 2>&1
   el "$(grep -h 'conv total' $OUT/${TAG}_conv_fetch$v.txt | cut -c1-400)"
 done
 
