@@ -87,6 +87,28 @@ __device__ __forceinline__ void gather_row16(uint32_t dst, const unsigned char* 
         : "memory");
 }
 
+// The same piece when an absent row may keep its stale shared-memory contents (its output lane is masked off in the
+// MMAs): the copy is GUARDED, not zero-filled -- no shared-memory write at all for an absent neighbour.
+template <int kRowBytes, int kDstOff, bool kBypassL1>
+__device__ __forceinline__ void gather_row16_skip(uint32_t dst, const unsigned char* base, int idx) {
+  if (kBypassL1)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 a;\n\t"
+        "setp.ge.s32 p, %2, 0;\n\t"
+        "mad.wide.s32 a, %2, %3, %1;\n\t"
+        "@p cp.async.cg.shared.global [%0+%4], [a], 16;\n\t}" ::"r"(dst),
+        "l"(base), "r"(idx), "n"(kRowBytes), "n"(kDstOff)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 a;\n\t"
+        "setp.ge.s32 p, %2, 0;\n\t"
+        "mad.wide.s32 a, %2, %3, %1;\n\t"
+        "@p cp.async.ca.shared.global [%0+%4], [a], 16;\n\t}" ::"r"(dst),
+        "l"(base), "r"(idx), "n"(kRowBytes), "n"(kDstOff)
+        : "memory");
+}
+
 constexpr int pow2_cols(int c) { return c <= 32 ? 32 : (c <= 64 ? 64 : (c <= 128 ? 128 : (c <= 256 ? 256 : 512))); }
 
 template <int CIN, int COUT>
@@ -110,21 +132,32 @@ struct TcCfg {
   static_assert(kSmemBytes <= 232448, "shared memory budget (227 KB per CTA)");
 };
 
-struct SlotMeta {
+struct alignas(16) SlotMeta {
   int last;  // 1 = last slot of its output tile
   int end;   // 1 = all tiles done
+  int pad[2];
+  uint4 off;  // scheme 4: disable-output-lane words of the slot (bit set = the row has no neighbour at this offset)
 };
 
-// kVer selects the fetch scheme: 1 = "lean" (round 2), 2 = "phase-aligned" (below: 4 instructions per copied row
-// instead of 9, weight stream on its own warp), 3 = 2 with L1-bypassing copies (cp.async.cg). All produce
-// bit-identical results; V3D_TC_FETCH=1|2|3 picks one.
+// kVer = scheme + 8 * cg + 16 * spin. scheme: 1 = "lean" (round 2); 2 = "phase-aligned" (4 instructions per copied
+// row instead of 9, weight stream on its own warp); 4 = 2 + absent neighbours are not copied at all: every slot but
+// the first of a tile runs lane-masked MMAs (tcgen05 disable-output-lane), so an absent row costs no shared-memory
+// write (CIN = 64 only); 5 = the same on top of scheme 1's row mapping. cg: copies bypass L1 (cp.async.cg). spin: mbarrier waits poll with test_wait instead of the
+// suspending try_wait. All variants produce bit-identical results; V3D_TC_FETCH / V3D_TC_CG / V3D_TC_WAIT pick one.
+constexpr bool tc_weight_warp(int kVer) { return (kVer & 7) == 2 || (kVer & 7) == 4; }
+constexpr int tc_threads(int kVer) { return 32 * (kWarpFetch0 + 8 + (tc_weight_warp(kVer) ? 1 : 0)); }
+
 template <int CIN, int COUT, int kFetchWarps, int kVer>
-__global__ void __launch_bounds__(32 * (kWarpFetch0 + kFetchWarps + (kVer >= 2 ? 1 : 0)), 1)
+__global__ void __launch_bounds__(tc_threads(kVer), 1)
 sparse_conv_tc_kernel(const unsigned char* __restrict__ feat, const unsigned char* __restrict__ wprep,
                       const int* __restrict__ nbr, int nbr_stride, const int* __restrict__ n_out_ptr, int out_cap,
                       int KV, const float* __restrict__ scale, const float* __restrict__ shift, int relu,
                       float* __restrict__ out, unsigned char* __restrict__ out_packed) {
   using C = TcCfg<CIN, COUT>;
+  constexpr int kScheme = kVer & 7;
+  constexpr bool kCg = ((kVer >> 3) & 1) != 0, kSpin = ((kVer >> 4) & 1) != 0;
+  static_assert(kScheme == 1 || kScheme == 2 || ((kScheme == 4 || kScheme == 5) && CIN == 64), "fetch scheme");
+  constexpr bool kSkip = kScheme == 4 || kScheme == 5;  // absent rows are not copied, lane-masked MMAs
   extern __shared__ unsigned char smem_raw[];
   // round up to 1024 B (SWIZZLE_128B atoms) by OFFSETTING the __shared__ array: casting through an integer
   // would make every later access a generic LD/ST instead of LDS/STS
@@ -140,6 +173,7 @@ sparse_conv_tc_kernel(const unsigned char* __restrict__ feat, const unsigned cha
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(meta + 8);
   uint32_t* fmask = tmem_slot + 1;  // [2] offsets used by the tile being staged (parity double buffer)
   int* neg_row = reinterpret_cast<int*>(tail + 512);  // [128] all -1 (scheme 2: rule row of a non-existent offset)
+  uint32_t* pres = reinterpret_cast<uint32_t*>(tail + 512);  // scheme 4 (never needs neg_row): [KV][4] presence words
   float* s_scale = reinterpret_cast<float*>(tail + 1024);
   float* s_shift = s_scale + COUT;
 
@@ -182,7 +216,7 @@ sparse_conv_tc_kernel(const unsigned char* __restrict__ feat, const unsigned cha
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
       const int a = it & 1;
-      mbar_wait(&acc_full[a], (it >> 1) & 1);
+      mbar_wait_as<kSpin>(&acc_full[a], (it >> 1) & 1);
       tc_fence_after();
       const int row = tile * kTileM + warp * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * C::kAccBufCols);
@@ -239,14 +273,14 @@ sparse_conv_tc_kernel(const unsigned char* __restrict__ feat, const unsigned cha
       bool tile_open = false;
       while (true) {
         const uint32_t s = q % C::kStages;
-        mbar_wait(&full[s], (q / C::kStages) & 1u);
+        mbar_wait_as<kSpin>(&full[s], (q / C::kStages) & 1u);
         const int m_last = meta[s].last, m_end = meta[s].end;
         if (m_end) {
           done = true;
           break;
         }
         if (!tile_open) {  // first slot of a tile: the accumulator buffer must have been drained
-          mbar_wait(&acc_empty[a], ((it >> 1) & 1) ^ 1);
+          mbar_wait_as<kSpin>(&acc_empty[a], ((it >> 1) & 1) ^ 1);
           tile_open = true;
         }
         fence_proxy_async();  // the A tiles were written by cp.async (generic proxy), the MMAs read them through
@@ -254,7 +288,20 @@ sparse_conv_tc_kernel(const unsigned char* __restrict__ feat, const unsigned cha
         const uint32_t st = ring_u32 + s * (uint32_t)C::kStageBytes;
         const uint64_t da1 = make_desc(st), da2 = make_desc(st + kATileBytes), db0 = make_desc(st + kABytes);
         const uint32_t d = tmem_base + (uint32_t)(a * C::kAccBufCols);
-        if (elect_one()) {
+        if (kSkip && accum != 0u) {
+          // not the first slot of the tile: rows without a neighbour at this offset were NOT copied (their A rows
+          // hold stale data) and their output lanes are switched off
+          const uint4 off = meta[s].off;
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < C::kKSteps; ks++) {
+              umma_bf16_ss_masked(d, da1 + 2u * ks, db0 + 2u * ks, idesc_wide, off.x, off.y, off.z, off.w);
+              umma_bf16_ss_masked(d, da2 + 2u * ks, db0 + 2u * ks, idesc_g1, off.x, off.y, off.z, off.w);
+            }
+            umma_commit(&empty[s]);
+            if (m_last) umma_commit(&acc_full[a]);
+          }
+        } else if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < C::kKSteps; ks++) {
             // K = 16 bf16 = 32 bytes along the swizzled row: the start address advances by 2 (16-byte units)
@@ -272,7 +319,7 @@ sparse_conv_tc_kernel(const unsigned char* __restrict__ feat, const unsigned cha
       }
       it++;
     }
-  } else if (kVer == 1) {
+  } else if (kScheme == 1 || kScheme == 5) {
     // =========================== fetchers (scheme 1) ===========================
     // What bounds this loop was measured on B200 by switching its parts off one at a time and by trying five
     // alternative fetch schemes (profiles/r02_conv_fetch_bisect.md): with no MMAs, no gather copies and no weight
@@ -324,7 +371,9 @@ sparse_conv_tc_kernel(const unsigned char* __restrict__ feat, const unsigned cha
       for (int j = 0; j < kPre; j++) {
         const int k = kpart + kParts * j;
         if (k < KV) idx_tile[k * kTileM + srow] = pre[j];
-        if (__any_sync(0xffffffffu, pre[j] >= 0)) mine |= 1u << k;
+        const uint32_t present = __ballot_sync(0xffffffffu, pre[j] >= 0);  // bit i = tile row 32 * (srow / 32) + i
+        if (present) mine |= 1u << k;
+        if (kSkip && lane == 0 && k < KV) pres[k * 4 + (srow >> 5)] = present;
       }
       if (lane == 0 && mine) atomicOr(&fmask[it & 1], mine);
       asm volatile("bar.sync 1, %0;" ::"n"(NF) : "memory");
@@ -332,15 +381,20 @@ sparse_conv_tc_kernel(const unsigned char* __restrict__ feat, const unsigned cha
       if (mask == 0) mask = 1u;  // cannot happen for a well-formed rule book; keeps the protocol total
       mask = group_mask<C::kGK>(mask);
       prefetch(tile + gridDim.x);
+      bool first = true;
       while (mask) {
         const int g = __ffs(mask) - 1;  // offset GROUP index = prepared image index
         mask &= mask - 1;
         const uint32_t s = q % C::kStages;
-        mbar_wait(&empty[s], ((q / C::kStages) & 1u) ^ 1u);
+        mbar_wait_as<kSpin>(&empty[s], ((q / C::kStages) & 1u) ^ 1u);
         const uint32_t st = s * (uint32_t)C::kStageBytes;
         if (gt == 0) {
           meta[s].last = (mask == 0);
           meta[s].end = 0;
+          if (kSkip) {  // rows without a neighbour at offset g (GK = 1: group = offset) -> output lanes switched off
+            const uint4 pm = *reinterpret_cast<const uint4*>(pres + g * 4);
+            meta[s].off = make_uint4(~pm.x, ~pm.y, ~pm.z, ~pm.w);
+          }
           mbar_arrive_expect_tx(&full[s], (uint32_t)C::kBBytes);
           bulk_g2s(ring_u32 + st + kABytes, wprep + (size_t)g * C::kBBytes, (uint32_t)C::kBBytes, &full[s]);
         }
@@ -353,15 +407,20 @@ sparse_conv_tc_kernel(const unsigned char* __restrict__ feat, const unsigned cha
         for (int i = 0; i < kRowsPerLane; i++) {  // (row0 + i) & 7 == i: the swizzle phase is a compile-time constant
           const bool ok = kv_ok && src[i] >= 0;
           const unsigned char* p = feat_lane + (size_t)(ok ? src[i] : 0) * kRowBytes;
-          cp_async16(dst_lane + st + (uint32_t)(i * 128 + ((unit ^ i) << 4)), p, ok ? 16u : 0u);
+          if (kSkip && !first && !ok) continue;  // lane-masked slot: an absent row is not written at all
+          if (kCg)
+            cp_async16_cg(dst_lane + st + (uint32_t)(i * 128 + ((unit ^ i) << 4)), p, ok ? 16u : 0u);
+          else
+            cp_async16(dst_lane + st + (uint32_t)(i * 128 + ((unit ^ i) << 4)), p, ok ? 16u : 0u);
         }
+        first = false;
         cp_async_arrive_noinc(&full[s]);  // arrives when this thread's copies have landed
         q++;
       }
     }
     {  // termination slot
       const uint32_t s = q % C::kStages;
-      mbar_wait(&empty[s], ((q / C::kStages) & 1u) ^ 1u);
+      mbar_wait_as<kSpin>(&empty[s], ((q / C::kStages) & 1u) ^ 1u);
       if (gt == 0) {
         meta[s].last = 1;
         meta[s].end = 1;
@@ -418,7 +477,9 @@ sparse_conv_tc_kernel(const unsigned char* __restrict__ feat, const unsigned cha
       for (int j = 0; j < kPre; j++) {
         const int k = kpart + kParts * j;
         if (k < KV) idx_tile[k * kTileM + spos] = pre[j];
-        if (__any_sync(0xffffffffu, pre[j] >= 0)) mine |= 1u << k;
+        const uint32_t present = __ballot_sync(0xffffffffu, pre[j] >= 0);  // bit i = tile row 32 * (srow / 32) + i
+        if (present) mine |= 1u << k;
+        if (kSkip && lane == 0 && k < KV) pres[k * 4 + (srow >> 5)] = present;
       }
       if (lane == 0 && mine) atomicOr(&fmask[it & 1], mine);
       asm volatile("bar.sync 1, %0;" ::"n"(NF + 32) : "memory");
@@ -426,6 +487,7 @@ sparse_conv_tc_kernel(const unsigned char* __restrict__ feat, const unsigned cha
       if (mask == 0) mask = 1u;
       mask = group_mask<C::kGK>(mask);
       prefetch(tile + gridDim.x);
+      bool first = true;
       while (mask) {
         const int g = __ffs(mask) - 1;
         mask &= mask - 1;
@@ -435,23 +497,35 @@ sparse_conv_tc_kernel(const unsigned char* __restrict__ feat, const unsigned cha
         const int4* idx_row = reinterpret_cast<const int4*>((kk < KV ? idx_tile + kk * kTileM : neg_row) + idx_pos);
         const int4 sa = idx_row[0], sb = idx_row[1];
         const uint32_t s = q % C::kStages;
-        mbar_wait(&empty[s], ((q / C::kStages) & 1u) ^ 1u);
+        mbar_wait_as<kSpin>(&empty[s], ((q / C::kStages) & 1u) ^ 1u);
         const uint32_t dst = dst_lane + s * (uint32_t)C::kStageBytes;
-        gather_row16<kRowBytes, 0 * 1024, kVer == 3>(dst, feat_lane, sa.x);
-        gather_row16<kRowBytes, 1 * 1024, kVer == 3>(dst, feat_lane, sa.y);
-        gather_row16<kRowBytes, 2 * 1024, kVer == 3>(dst, feat_lane, sa.z);
-        gather_row16<kRowBytes, 3 * 1024, kVer == 3>(dst, feat_lane, sa.w);
-        gather_row16<kRowBytes, 4 * 1024, kVer == 3>(dst, feat_lane, sb.x);
-        gather_row16<kRowBytes, 5 * 1024, kVer == 3>(dst, feat_lane, sb.y);
-        gather_row16<kRowBytes, 6 * 1024, kVer == 3>(dst, feat_lane, sb.z);
-        gather_row16<kRowBytes, 7 * 1024, kVer == 3>(dst, feat_lane, sb.w);
+        if (kSkip && !first) {  // lane-masked slot: absent rows are simply not copied
+          gather_row16_skip<kRowBytes, 0 * 1024, kCg>(dst, feat_lane, sa.x);
+          gather_row16_skip<kRowBytes, 1 * 1024, kCg>(dst, feat_lane, sa.y);
+          gather_row16_skip<kRowBytes, 2 * 1024, kCg>(dst, feat_lane, sa.z);
+          gather_row16_skip<kRowBytes, 3 * 1024, kCg>(dst, feat_lane, sa.w);
+          gather_row16_skip<kRowBytes, 4 * 1024, kCg>(dst, feat_lane, sb.x);
+          gather_row16_skip<kRowBytes, 5 * 1024, kCg>(dst, feat_lane, sb.y);
+          gather_row16_skip<kRowBytes, 6 * 1024, kCg>(dst, feat_lane, sb.z);
+          gather_row16_skip<kRowBytes, 7 * 1024, kCg>(dst, feat_lane, sb.w);
+        } else {
+          gather_row16<kRowBytes, 0 * 1024, kCg>(dst, feat_lane, sa.x);
+          gather_row16<kRowBytes, 1 * 1024, kCg>(dst, feat_lane, sa.y);
+          gather_row16<kRowBytes, 2 * 1024, kCg>(dst, feat_lane, sa.z);
+          gather_row16<kRowBytes, 3 * 1024, kCg>(dst, feat_lane, sa.w);
+          gather_row16<kRowBytes, 4 * 1024, kCg>(dst, feat_lane, sb.x);
+          gather_row16<kRowBytes, 5 * 1024, kCg>(dst, feat_lane, sb.y);
+          gather_row16<kRowBytes, 6 * 1024, kCg>(dst, feat_lane, sb.z);
+          gather_row16<kRowBytes, 7 * 1024, kCg>(dst, feat_lane, sb.w);
+        }
+        first = false;
         cp_async_arrive_noinc(&full[s]);
         q++;
       }
     }
     {  // termination slot: the fetchers' share of the arrivals
       const uint32_t s = q % C::kStages;
-      mbar_wait(&empty[s], ((q / C::kStages) & 1u) ^ 1u);
+      mbar_wait_as<kSpin>(&empty[s], ((q / C::kStages) & 1u) ^ 1u);
       mbar_arrive(&full[s]);
     }
   } else {
@@ -472,10 +546,14 @@ sparse_conv_tc_kernel(const unsigned char* __restrict__ feat, const unsigned cha
         const int g = __ffs(mask) - 1;
         mask &= mask - 1;
         const uint32_t s = q % C::kStages;
-        mbar_wait(&empty[s], ((q / C::kStages) & 1u) ^ 1u);
+        mbar_wait_as<kSpin>(&empty[s], ((q / C::kStages) & 1u) ^ 1u);
         if (lane == 0) {
           meta[s].last = (mask == 0);
           meta[s].end = 0;
+          if (kSkip) {  // rows without a neighbour at offset g (GK = 1: group = offset) -> lanes switched off
+            const uint4 pm = *reinterpret_cast<const uint4*>(pres + g * 4);
+            meta[s].off = make_uint4(~pm.x, ~pm.y, ~pm.z, ~pm.w);
+          }
           mbar_arrive_expect_tx(&full[s], (uint32_t)C::kBBytes);
           bulk_g2s(ring_u32 + s * (uint32_t)C::kStageBytes + kABytes, wprep + (size_t)g * C::kBBytes,
                    (uint32_t)C::kBBytes, &full[s]);
@@ -486,7 +564,7 @@ sparse_conv_tc_kernel(const unsigned char* __restrict__ feat, const unsigned cha
     }
     {  // termination slot
       const uint32_t s = q % C::kStages;
-      mbar_wait(&empty[s], ((q / C::kStages) & 1u) ^ 1u);
+      mbar_wait_as<kSpin>(&empty[s], ((q / C::kStages) & 1u) ^ 1u);
       if (lane == 0) {
         meta[s].last = 1;
         meta[s].end = 1;
@@ -553,16 +631,20 @@ __global__ void feature_pack_kernel(const float* __restrict__ feat, const int* _
   }
 }
 
-// Fetch scheme of the tensor-core kernel: V3D_TC_FETCH=1 "lean" (round 2), 2 phase-aligned, 3 = 2 + cp.async.cg.
-constexpr int kDefaultFetchScheme = 1;
-inline int tc_fetch_scheme() {
-  static const int v = [] {
-    const char* e = getenv("V3D_TC_FETCH");
-    if (e && e[0] == '1') return 1;
-    if (e && e[0] == '2') return 2;
-    if (e && e[0] == '3') return 3;
-    return kDefaultFetchScheme;
-  }();
+// Variant of the tensor-core kernel (see the kernel's header): V3D_TC_FETCH = 1 | 2 | 4 | 5, V3D_TC_CG = 0 | 1,
+// V3D_TC_WAIT = 0 | 1. Read once per process.
+constexpr int kDefaultFetchScheme = 1, kDefaultCg = 0, kDefaultSpin = 0;
+inline int tc_env_digit(const char* name, int dflt, const char* allowed) {
+  const char* e = getenv(name);
+  if (e && e[0] && !e[1])
+    for (const char* a = allowed; *a; a++)
+      if (*a == e[0]) return e[0] - '0';
+  return dflt;
+}
+inline int tc_variant() {
+  static const int v = tc_env_digit("V3D_TC_FETCH", kDefaultFetchScheme, "1245") +
+                       8 * tc_env_digit("V3D_TC_CG", kDefaultCg, "01") +
+                       16 * tc_env_digit("V3D_TC_WAIT", kDefaultSpin, "01");
   return v;
 }
 
@@ -579,7 +661,7 @@ int launch_tc_ver(const unsigned char* feat, const unsigned char* wprep, const i
   }
   const int tiles_cap = ceil_div(out_cap, kTileM);
   const int grid = tiles_cap < kNumSMs ? (tiles_cap > 0 ? tiles_cap : 1) : kNumSMs;
-  sparse_conv_tc_kernel<CIN, COUT, 8, kVer><<<grid, 32 * (kWarpFetch0 + 8 + (kVer >= 2 ? 1 : 0)), C::kSmemBytes, st>>>(
+  sparse_conv_tc_kernel<CIN, COUT, 8, kVer><<<grid, tc_threads(kVer), C::kSmemBytes, st>>>(
       feat, wprep, nbr, nbr_stride, n_out, out_cap, KV, scale, shift, relu, out, out_packed);
   return check_launch();
 }
@@ -588,14 +670,32 @@ template <int CIN, int COUT>
 int launch_tc(const unsigned char* feat, const unsigned char* wprep, const int* nbr, int nbr_stride, const int* n_out,
               int out_cap, int KV, const float* scale, const float* shift, int relu, float* out,
               unsigned char* out_packed, cudaStream_t st) {
-  if (tc_fetch_scheme() == 1)
-    return launch_tc_ver<CIN, COUT, 1>(feat, wprep, nbr, nbr_stride, n_out, out_cap, KV, scale, shift, relu, out,
-                                       out_packed, st);
-  if (tc_fetch_scheme() == 3)
-    return launch_tc_ver<CIN, COUT, 3>(feat, wprep, nbr, nbr_stride, n_out, out_cap, KV, scale, shift, relu, out,
-                                       out_packed, st);
-  return launch_tc_ver<CIN, COUT, 2>(feat, wprep, nbr, nbr_stride, n_out, out_cap, KV, scale, shift, relu, out,
-                                     out_packed, st);
+  int v = tc_variant();
+  if (((v & 7) == 4 || (v & 7) == 5) && CIN != 64) v = (v & ~7) | 1;  // schemes 4, 5: CIN = 64 (one offset per slot) only
+#define V3D_TC_VER(VER)                                                                                           \
+  if (v == (VER))                                                                                                 \
+    return launch_tc_ver<CIN, COUT, (VER)>(feat, wprep, nbr, nbr_stride, n_out, out_cap, KV, scale, shift, relu, out, \
+                                           out_packed, st);
+  V3D_TC_VER(1)
+  V3D_TC_VER(1 + 8)
+  V3D_TC_VER(1 + 16)
+  V3D_TC_VER(1 + 8 + 16)
+  V3D_TC_VER(2)
+  V3D_TC_VER(2 + 8)
+  V3D_TC_VER(2 + 16)
+  V3D_TC_VER(2 + 8 + 16)
+  if constexpr (CIN == 64) {
+    V3D_TC_VER(4)
+    V3D_TC_VER(4 + 8)
+    V3D_TC_VER(4 + 16)
+    V3D_TC_VER(4 + 8 + 16)
+    V3D_TC_VER(5)
+    V3D_TC_VER(5 + 8)
+    V3D_TC_VER(5 + 16)
+    V3D_TC_VER(5 + 8 + 16)
+  }
+#undef V3D_TC_VER
+  return V3D_ERR_INVALID_ARGUMENT;
 }
 
 inline bool tc_supported(int KV, int Cin, int Cout) {
