@@ -526,6 +526,14 @@ def c3_block(args, dev, hbm_peak):
             "active_sites_per_level": rows, "per_op": table, "cpu_baseline": cpu}
 
 
+def _conv_variant():
+    """fetch scheme / L1 bypass / wait flavour of the tcgen05 kernel in this process (csrc/sparse_conv_tc.cu)"""
+    from vision3d_b200 import _lib
+    v = _lib.load().v3d_sparse_conv_tc_variant()
+    return {"fetch_scheme": v & 7, "cp_async_cg": (v >> 3) & 1, "spin_wait": (v >> 4) & 1,
+            "note": "scheme 4 (Cin = 64 layers): absent neighbours are not copied, lane-masked MMAs; other layers scheme 1"}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -639,6 +647,7 @@ def run_b200(args):
                        "sparse_conv": "exact-fp32 SIMT" if args.simt else
                        "tcgen05 kind::f16, bf16x3 split (h1*g1 + h1*g2 + h2*g1), fp32 accumulate in TMEM, all 14 layers "
                        "(the 4-channel input layer is zero-padded to 16 channels)",
+                       "sparse_conv_variant": _conv_variant(),
                        "rpn": "torch/cuDNN fp32 storage, TF32 tensor-core math allowed=%s, mode=%s; parity-tested in "
                               "this mode (tests/test_gpu_bench_config.py: RPN <= 1e-2 of map scale vs fp32 CPU)"
                               % (torch.backends.cudnn.allow_tf32, args.rpn),

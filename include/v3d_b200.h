@@ -203,6 +203,9 @@ V3D_API int v3d_sparse_conv_fwd(const float* feat, const float* weight, const in
  * shared-memory image the kernel streams with 1-D TMA:
  *   v3d_sparse_conv_prepared_bytes returns 0 for shapes only the exact-fp32 path supports (Cin < 16 ...).
  * Supported: kernel_volume <= 27, Cin and Cout in {16, 32, 64}. */
+V3D_API int v3d_sparse_conv_tc_variant(void); /* diagnostic: fetch scheme + 8 * cg + 16 * spin of the tcgen05 kernel
+                                                 this process runs (V3D_TC_FETCH / V3D_TC_CG / V3D_TC_WAIT or the
+                                                 built-in defaults, csrc/sparse_conv_tc.cu); no reference counterpart */
 V3D_API size_t v3d_sparse_conv_prepared_bytes(int kernel_volume, int Cin, int Cout);
 V3D_API int v3d_sparse_conv_prepare(const float* weight, int kernel_volume, int Cin, int Cout, void* prepared,
                                     size_t prepared_bytes, v3d_stream_t stream);

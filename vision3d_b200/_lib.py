@@ -19,6 +19,7 @@ SIGNATURES = {
     "v3d_last_cuda_error": (ctypes.c_char_p, []),
     "v3d_cudart_version": (c_int, []),
     "v3d_check_device": (c_int, []),
+    "v3d_sparse_conv_tc_variant": (c_int, []),
     "v3d_box_iou_rotated": (c_int, [P, c_int, P, c_int, P, P]),
     "v3d_nms_rotated_workspace_bytes": (c_size_t, [c_int]),
     "v3d_nms_rotated": (c_int, [P, P, c_int, c_float, P, P, P, c_size_t, P]),

@@ -633,7 +633,9 @@ __global__ void feature_pack_kernel(const float* __restrict__ feat, const int* _
 
 // Variant of the tensor-core kernel (see the kernel's header): V3D_TC_FETCH = 1 | 2 | 4 | 5, V3D_TC_CG = 0 | 1,
 // V3D_TC_WAIT = 0 | 1. Read once per process.
-constexpr int kDefaultFetchScheme = 1, kDefaultCg = 0, kDefaultSpin = 0;
+// Defaults = the fastest parity-green variant of the matrix measured on B200 (profiles/r02x_conv_variants.txt):
+// CIN = 64 layers: scheme 4 + cg (conv total 1615 us against 1787 us for scheme 1); other layers: scheme 1 + cg.
+constexpr int kDefaultFetchScheme = 4, kDefaultCg = 1, kDefaultSpin = 0;
 inline int tc_env_digit(const char* name, int dflt, const char* allowed) {
   const char* e = getenv(name);
   if (e && e[0] && !e[1])
@@ -706,6 +708,8 @@ inline bool tc_supported(int KV, int Cin, int Cout) {
 }  // namespace v3d
 
 using namespace v3d;
+
+extern "C" int v3d_sparse_conv_tc_variant(void) { return tc_variant(); }
 
 extern "C" size_t v3d_sparse_conv_prepared_bytes(int kernel_volume, int Cin, int Cout) {
   if (!tc_supported(kernel_volume, Cin, Cout)) return 0;  // 0 = this shape runs on the exact-fp32 SIMT path
