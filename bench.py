@@ -409,6 +409,12 @@ def per_op_table(eng, h_sets, hbm_peak, peak_kind):
         if t:
             roofline["traffic"] = int(t["dram_bytes_per_launch"])
             roofline["traffic_source"] = t.get("source")
+    if fam == "sparse_conv_fwd":
+        # what actually bounds this kernel (ncu counters): neither HBM nor the tensor pipe
+        roofline["limiter"] = ("shared-memory crossbar: SS-operand MMAs move 104 KB per K=64 slot (A written + read, weight "
+                               "image written + read) at 128 B/clk/SM = 832 clk per slot against 444 clk of MMAs; measured "
+                               "0.92 wavefronts/clk before, 0.71 after absent neighbours stopped being copied "
+                               "(profiles/r02y_conv_counters.md, profiles/r02x_conv_counters.md)")
     fams = {k: {"us": round(v["us"], 1), "gbs": round(v["bytes"] / v["us"] / 1e3, 1),
                 "frac": round(v["bytes"] / v["us"] / 1e3 / hbm_peak, 4), "launches": v["n"]} for k, v in groups.items()}
     return table, roofline, fams, rows, counts
