@@ -36,3 +36,37 @@ def test_phase_aligned_fetch_covers_the_a_tiles_exactly_once(cin):
                 # i.e. bytes [2 * (8u % cin), +16) of the h1 half (part 0) or the h2 half (part 1) of the packed source row
                 assert off == (8 * u) // cin and src_byte == part * 2 * cin + 2 * ((8 * u) % cin)
     assert len(written) == 2 * K_TILE_M * 8
+
+
+def test_conv_variant_selection_from_environment():
+    """v3d_sparse_conv_tc_variant (no device needed): fetch scheme + 8 * cg + 16 * spin; unknown values fall back to the
+    built-in defaults (scheme 4 + cp.async.cg, the variant measured fastest: profiles/r02x_conv_variants.txt)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path.insert(0, %r); from vision3d_b200 import _lib; "
+            "print(_lib.load().v3d_sparse_conv_tc_variant())" % root)
+
+    def variant(**env):
+        e = {k: v for k, v in os.environ.items() if not k.startswith("V3D_TC_")}
+        e.update(env)
+        return int(subprocess.run([sys.executable, "-c", code], env=e, capture_output=True, text=True,
+                                  check=True).stdout.strip())
+
+    assert variant() == 4 + 8
+    assert variant(V3D_TC_FETCH="1", V3D_TC_CG="0") == 1
+    assert variant(V3D_TC_FETCH="2", V3D_TC_WAIT="1") == 2 + 8 + 16
+    assert variant(V3D_TC_FETCH="7", V3D_TC_CG="x") == 4 + 8
+
+
+def test_bench_reports_the_conv_variant():
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+
+    v = bench._conv_variant()
+    assert set(v) >= {"fetch_scheme", "cp_async_cg", "spin_wait"} and v["fetch_scheme"] in (1, 2, 4, 5)
