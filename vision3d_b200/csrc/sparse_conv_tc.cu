@@ -13,7 +13,7 @@
 // 16-byte cp.async straight into the 128B-swizzled K-major A tiles the MMAs read from shared memory.
 // No conversion pass, no register staging, no TMEM operand.
 //
-// One persistent CTA per SM, warp specialised (416 threads):
+// One persistent CTA per SM, warp specialised (416 threads; 448 with the weight warp of schemes 2 / 4):
 //   warps 0-3  epilogue   : tcgen05.ld the 128 x COUT fp32 accumulator halves (lane = output row), add
 //                           them, apply scale/shift/ReLU, store the row as fp32 and/or packed bf16x2
 //   warp  4    MMA issuer : warp-uniform loop, one elected lane issues per pipeline slot (K = 64) 2*4
@@ -22,13 +22,17 @@
 //                           the stage and publishes the accumulator through mbarriers
 //   warps 5-12 fetchers   : stage the tile's rule rows in shared memory (the next tile's are prefetched
 //                           into registers), find the kernel offsets the tile uses, and for every slot
-//                           gather the neighbour rows (zero-fill for missing neighbours) with cp.async into
-//                           the stage's A tiles while one thread streams the slot's weight image with a
-//                           1-D TMA bulk copy. Completion is asynchronous (cp.async.mbarrier.arrive on the
-//                           stage's full barrier), so up to kStages slots of global-load latency are in
-//                           flight and the fetchers never wait for their own loads.
-// Measured instruction costs on B200 (scripts/mma_probe.cu): one M=128 MMA costs max(47, N/2) clk for
-// every operand kind/source, so a slot is 4*(64+47) = 444 clk for COUT = 64 (3xTF32 needed 888).
+//                           gather the neighbour rows with cp.async into the stage's A tiles. Completion is
+//                           asynchronous (cp.async.mbarrier.arrive on the stage's full barrier), so up to kStages
+//                           slots of global-load latency are in flight and the fetchers never wait for their own loads.
+//   warp  13   weights    : (schemes 2 / 4) per slot the meta record, the expect_tx arrival and the 1-D TMA bulk copy
+//                           of the slot's weight image; in scheme 1 thread 0 of the fetchers does this.
+// What bounds it (ncu): the SHARED-MEMORY CROSSBAR. With SS operands a Cin = Cout = 64 slot moves
+// 104 KB through shared memory (A written 32 KB + read 32 KB, weight image written 16 KB + read 24 KB) = 832
+// wavefronts at 128 B/clk, against 444 clk of MMAs (one M=128 MMA costs max(47, N/2) clk, scripts/mma_probe.cu);
+// measured 0.92 wavefronts per clk with every tile row copied or zero-filled. The shipped scheme 4 therefore does
+// not write absent neighbours at all (57 % of the rows): the first slot of a tile zero-fills and initialises the
+// accumulator, later slots copy present rows only and run lane-masked MMAs (tcgen05 disable-output-lane).
 // Output rows are written exactly once (no atomics, deterministic).
 //
 // Operand layout (K-major, SWIZZLE_128B, bf16): a tile row is 64 K-elements = 128 bytes; 8-row groups are
@@ -321,16 +325,11 @@ sparse_conv_tc_kernel(const unsigned char* __restrict__ feat, const unsigned cha
     }
   } else if (kScheme == 1 || kScheme == 5) {
     // =========================== fetchers (scheme 1) ===========================
-    // What bounds this loop was measured on B200 by switching its parts off one at a time and by trying five
-    // alternative fetch schemes (profiles/r02_conv_fetch_bisect.md): with no MMAs, no gather copies and no weight
-    // stream the control skeleton alone still runs at ~700 clk per K=64 slot (full kernel ~900, the MMAs 444);
-    // every instruction added to the per-slot path of a fetch warp shows up 1:1 at ~5 clk (two fetch warps per
-    // scheduler: nothing hides a dependent chain) and every LDGSTS warp instruction costs ~8 clk of LSU time.
-    // Bytes, wavefronts, L2 and the tensor pipe are all far from their limits, so skipping absent rows
-    // (predicated, compacted with lane-masked MMAs, per-stage or alternating warp groups) lost more in added
-    // instructions than it saved. The loop is therefore kept as short as it gets: a lane's 8 rows are CONSECUTIVE,
-    // their rule entries arrive as two 128-bit shared loads, there is one LDGSTS form (no cache-policy twin), no
-    // per-row control flow, and every tile row is copied or zero-filled.
+    // The round-2 "lean" loop: a lane's 8 rows are CONSECUTIVE, their rule entries arrive as two 128-bit shared
+    // loads, one LDGSTS form, every tile row is copied or zero-filled (~137 SASS instructions per slot per warp, a
+    // dependent chain of ~5 clk per instruction: profiles/r02_conv_fetch_bisect.md). It ships for the K-stacked layers
+    // (CIN = 16 / 32); scheme 5 = the same with absent rows skipped (measured slower: the per-row branches lengthen
+    // the chain, profiles/r02x_conv_variants.txt).
     constexpr int NF = kFetchWarps * 32;
     static_assert(kFetchWarps == 8, "16 tile rows per fetch warp");
     constexpr int kRowBytes = 4 * CIN;  // packed source row: [h1 (2*CIN bytes) | h2 (2*CIN bytes)]
